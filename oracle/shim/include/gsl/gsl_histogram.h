@@ -1,0 +1,1 @@
+/* empty: gsl is included by data_types.h but unused by the Solver */
