@@ -1,0 +1,226 @@
+// FP64 cooperative FFT engine for sm_100a: radix-2/4/8/16 butterflies in registers, twiddles from an
+// L1-resident table, digit exchange through shared memory.  Replaces the FFTW codelets behind
+// fftw_mpi_execute_dft_r2c/c2r (reference call sites solver.c:656,658,683).
+//
+// A length-N transform is executed by TP threads in 2 or 3 radix passes (N = R1*R2[*R3]):
+//   pass 1  thread b loads x[b + j*N/R1] (unit stride across threads -> coalesced), R1-point DFT,
+//           twiddle W_N^{b*k1}, scatter to shared memory row k1
+//   pass 2  (3-pass plans) in-place R2-point DFTs inside each row, twiddle W_{N/R1}^{m2*k1'}
+//   last    thread b = k1 + R1*k1' gathers its R_last contiguous elements, DFT, and owns outputs
+//           X[b + j*N/R_last] (again unit stride across threads)
+// so input and output are both in natural order and both coalesced.  Shared-memory index i is
+// padded to i + i/(N/R1) which makes every access pattern above bank-conflict free for 16-byte
+// elements.  Everything is __host__ __device__ so tests/host_emul can run the passes on the CPU.
+#pragma once
+#include <cuda_runtime.h>
+
+#define NSB_HD __host__ __device__ __forceinline__
+
+typedef double2 cplx;
+
+constexpr int FWD = -1;  // exp(-i ...)  r2c direction
+constexpr int INV = +1;  // exp(+i ...)  c2r direction
+
+NSB_HD cplx mk(double x, double y) { cplx r; r.x = x; r.y = y; return r; }
+NSB_HD cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
+NSB_HD cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+NSB_HD cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+NSB_HD cplx cconj(cplx a) { return mk(a.x, -a.y); }
+NSB_HD cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
+// multiply by -i (forward) or +i (inverse)
+template <int DIR> NSB_HD cplx rot(cplx a) { return DIR == FWD ? mk(a.y, -a.x) : mk(-a.y, a.x); }
+// multiply by exp(DIR * i * theta) given (c, s) = (cos theta, sin theta)
+template <int DIR> NSB_HD cplx cmul_cs(cplx a, double c, double s) {
+    return DIR == FWD ? mk(a.x * c + a.y * s, a.y * c - a.x * s) : mk(a.x * c - a.y * s, a.y * c + a.x * s);
+}
+// table holds exp(-2 pi i m / N); conjugate for the inverse direction
+template <int DIR> NSB_HD cplx twid(const cplx* __restrict__ tw, int idx) {
+    cplx w = tw[idx];
+    if (DIR == INV) w.y = -w.y;
+    return w;
+}
+
+template <int DIR> NSB_HD void dft2(cplx& a, cplx& b) {
+    cplx t = csub(a, b);
+    a = cadd(a, b);
+    b = t;
+}
+
+template <int DIR> NSB_HD void dft4(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {
+    cplx t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = rot<DIR>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+#define NSB_SQRT1_2 0.70710678118654752440
+#define NSB_COS_PI_8 0.92387953251128675613
+#define NSB_SIN_PI_8 0.38268343236508977173
+
+template <int R, int DIR> struct Dft;
+
+template <int DIR> struct Dft<2, DIR> {
+    static NSB_HD void run(cplx* v) { dft2<DIR>(v[0], v[1]); }
+};
+template <int DIR> struct Dft<4, DIR> {
+    static NSB_HD void run(cplx* v) { dft4<DIR>(v[0], v[1], v[2], v[3]); }
+};
+template <int DIR> struct Dft<8, DIR> {
+    static NSB_HD void run(cplx* v) {
+        // even / odd 4-point transforms
+        dft4<DIR>(v[0], v[2], v[4], v[6]);
+        dft4<DIR>(v[1], v[3], v[5], v[7]);
+        // odd outputs O[k] live in v[1], v[3], v[5], v[7]; apply W8^k
+        cplx o1 = cmul_cs<DIR>(v[3], NSB_SQRT1_2, NSB_SQRT1_2);
+        cplx o2 = rot<DIR>(v[5]);
+        cplx o3 = cmul_cs<DIR>(v[7], -NSB_SQRT1_2, NSB_SQRT1_2);
+        cplx e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+        v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+        v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+        v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+        v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+    }
+};
+template <int DIR> struct Dft<16, DIR> {
+    static NSB_HD void run(cplx* v) {
+        // E_r[k] = DFT4 over v[r + 4m]; result k stored at v[r + 4k]
+        dft4<DIR>(v[0], v[4], v[8], v[12]);
+        dft4<DIR>(v[1], v[5], v[9], v[13]);
+        dft4<DIR>(v[2], v[6], v[10], v[14]);
+        dft4<DIR>(v[3], v[7], v[11], v[15]);
+        // k = 0: no twiddles
+        cplx a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+        dft4<DIR>(a0, a1, a2, a3);
+        // k = 1: W16^1, W16^2, W16^3
+        cplx b0 = v[4];
+        cplx b1 = cmul_cs<DIR>(v[5], NSB_COS_PI_8, NSB_SIN_PI_8);
+        cplx b2 = cmul_cs<DIR>(v[6], NSB_SQRT1_2, NSB_SQRT1_2);
+        cplx b3 = cmul_cs<DIR>(v[7], NSB_SIN_PI_8, NSB_COS_PI_8);
+        dft4<DIR>(b0, b1, b2, b3);
+        // k = 2: W16^2, W16^4, W16^6
+        cplx c0 = v[8];
+        cplx c1 = cmul_cs<DIR>(v[9], NSB_SQRT1_2, NSB_SQRT1_2);
+        cplx c2 = rot<DIR>(v[10]);
+        cplx c3 = cmul_cs<DIR>(v[11], -NSB_SQRT1_2, NSB_SQRT1_2);
+        dft4<DIR>(c0, c1, c2, c3);
+        // k = 3: W16^3, W16^6, W16^9
+        cplx d0 = v[12];
+        cplx d1 = cmul_cs<DIR>(v[13], NSB_SIN_PI_8, NSB_COS_PI_8);
+        cplx d2 = cmul_cs<DIR>(v[14], -NSB_SQRT1_2, NSB_SQRT1_2);
+        cplx d3 = cmul_cs<DIR>(v[15], -NSB_COS_PI_8, -NSB_SIN_PI_8);
+        dft4<DIR>(d0, d1, d2, d3);
+        // X[k + 4m] = m-th output of group k
+        v[0] = a0; v[4] = a1; v[8] = a2;  v[12] = a3;
+        v[1] = b0; v[5] = b1; v[9] = b2;  v[13] = b3;
+        v[2] = c0; v[6] = c1; v[10] = c2; v[14] = c3;
+        v[3] = d0; v[7] = d1; v[11] = d2; v[15] = d3;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Plans: N = R1 * R2 * R3 (R3 == 1 for two-pass plans)
+// ---------------------------------------------------------------------------------------------
+template <int N_, int R1_, int R2_, int R3_> struct FftPlan {
+    static constexpr int N = N_, R1 = R1_, R2 = R2_, R3 = R3_;
+    static constexpr int PASSES = (R3_ > 1) ? 3 : 2;
+    static constexpr int M1 = N_ / R1_;                  // row length after pass 1
+    static constexpr int RL = (R3_ > 1) ? R3_ : R2_;     // radix of the last pass
+    static constexpr int NB1 = N_ / R1_;                 // butterflies per pass
+    static constexpr int NB2 = N_ / R2_;
+    static constexpr int NBL = N_ / RL;
+    static constexpr int NPAD = N_ + R1_;                // padded shared-memory elements per transform
+    static_assert(R1_ * R2_ * R3_ == N_, "bad plan");
+};
+
+// throughput plans (strided x / y passes): large radices, few passes
+template <int N> struct BigPlan;
+template <> struct BigPlan<16> { typedef FftPlan<16, 4, 4, 1> type; };
+template <> struct BigPlan<32> { typedef FftPlan<32, 4, 8, 1> type; };
+template <> struct BigPlan<64> { typedef FftPlan<64, 8, 8, 1> type; };
+template <> struct BigPlan<128> { typedef FftPlan<128, 8, 16, 1> type; };
+template <> struct BigPlan<256> { typedef FftPlan<256, 16, 16, 1> type; };
+template <> struct BigPlan<512> { typedef FftPlan<512, 8, 8, 8> type; };
+template <> struct BigPlan<1024> { typedef FftPlan<1024, 8, 8, 16> type; };
+
+// z-pencil plans: R1 is the smallest radix so pass 1 has exactly one butterfly per thread with
+// TP = N/R1 threads per transform (later passes use a subset of the threads)
+template <int N> struct ZPlan;
+template <> struct ZPlan<16> { typedef FftPlan<16, 4, 4, 1> type; };
+template <> struct ZPlan<32> { typedef FftPlan<32, 4, 8, 1> type; };
+template <> struct ZPlan<64> { typedef FftPlan<64, 4, 4, 4> type; };
+template <> struct ZPlan<128> { typedef FftPlan<128, 4, 4, 8> type; };
+template <> struct ZPlan<256> { typedef FftPlan<256, 4, 8, 8> type; };
+template <> struct ZPlan<512> { typedef FftPlan<512, 8, 8, 8> type; };
+template <> struct ZPlan<1024> { typedef FftPlan<1024, 8, 8, 16> type; };
+
+template <class P> NSB_HD int padi(int i) { return i + i / P::M1; }
+
+// ---------------------------------------------------------------------------------------------
+// Passes.  `sm` points at element 0 of this transform's shared-memory buffer, STRIDE is the distance
+// (in cplx) between consecutive elements (T for tile-interleaved pencils, 1 for a private buffer).
+// ---------------------------------------------------------------------------------------------
+template <class P, int DIR, int STRIDE, class Ld>
+NSB_HD void fft_pass1(int b, cplx* sm, const cplx* __restrict__ tw, Ld ld) {
+    cplx v[P::R1];
+#pragma unroll
+    for (int j = 0; j < P::R1; ++j) v[j] = ld(b + j * P::M1);
+    Dft<P::R1, DIR>::run(v);
+#pragma unroll
+    for (int k1 = 1; k1 < P::R1; ++k1) v[k1] = cmul(v[k1], twid<DIR>(tw, b * k1));
+#pragma unroll
+    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * (P::M1 + 1) + b) * STRIDE] = v[k1];
+}
+
+// pass 1 on values already in registers (used when the loader needs a barrier before the scatter)
+template <class P, int DIR> NSB_HD void fft_pass1_regs(int b, cplx* v, const cplx* __restrict__ tw) {
+    Dft<P::R1, DIR>::run(v);
+#pragma unroll
+    for (int k1 = 1; k1 < P::R1; ++k1) v[k1] = cmul(v[k1], twid<DIR>(tw, b * k1));
+}
+template <class P, int STRIDE> NSB_HD void fft_pass1_scatter(int b, cplx* sm, const cplx* v) {
+#pragma unroll
+    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * (P::M1 + 1) + b) * STRIDE] = v[k1];
+}
+
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass2(int b, cplx* sm, const cplx* __restrict__ tw) {
+    static_assert(P::PASSES == 3, "pass2 only exists in 3-pass plans");
+    const int k1 = b / P::R3, m2 = b % P::R3;
+    const int base = k1 * (P::M1 + 1) + m2;
+    cplx v[P::R2];
+#pragma unroll
+    for (int j = 0; j < P::R2; ++j) v[j] = sm[(base + j * P::R3) * STRIDE];
+    Dft<P::R2, DIR>::run(v);
+#pragma unroll
+    for (int kp = 1; kp < P::R2; ++kp) v[kp] = cmul(v[kp], twid<DIR>(tw, P::R1 * m2 * kp));
+#pragma unroll
+    for (int kp = 0; kp < P::R2; ++kp) sm[(base + kp * P::R3) * STRIDE] = v[kp];
+}
+
+// last pass: v[k2] is output element  b + k2 * P::NBL
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass_last(int b, const cplx* sm, cplx* v) {
+    const int k1 = b % P::R1, kp = b / P::R1;
+    const int base = k1 * (P::M1 + 1) + kp * P::RL;
+#pragma unroll
+    for (int m = 0; m < P::RL; ++m) v[m] = sm[(base + m) * STRIDE];
+    Dft<P::RL, DIR>::run(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two real transforms packed into one complex transform (z = a + i b).
+// ---------------------------------------------------------------------------------------------
+// c2r: element n of the full Hermitian spectrum built from the two half spectra A, B (k = 0..N/2).
+// Like FFTW's c2r the imaginary parts of the k = 0 and k = N/2 entries are ignored.
+template <int N> NSB_HD cplx pack_hermitian(int n, cplx A, cplx B) {
+    // A, B are the half-spectrum entries at k = (n <= N/2 ? n : N - n)
+    if (n == 0 || n == N / 2) { A.y = 0.0; B.y = 0.0; }
+    if (n > N / 2) { A.y = -A.y; B.y = -B.y; }
+    return mk(A.x - B.y, A.y + B.x);
+}
+// r2c: half-spectrum entries of the two real inputs from Z(k) and Z(N-k)
+NSB_HD void unpack_pair(cplx Zk, cplx Zm, cplx& A, cplx& B) {
+    A = mk(0.5 * (Zk.x + Zm.x), 0.5 * (Zk.y - Zm.y));
+    B = mk(0.5 * (Zk.y + Zm.y), -0.5 * (Zk.x - Zm.x));
+}

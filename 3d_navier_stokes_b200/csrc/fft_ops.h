@@ -1,0 +1,21 @@
+// Per-size dispatch table between the C-ABI layer (nsb200.cu) and the templated FFT kernels, which are
+// instantiated one grid size per translation unit (fft_inst.cu compiled with -DNSB_N=...).
+#pragma once
+#include "fft_kernels.cuh"
+
+enum { NSB_Z_C2R = 0, NSB_Z_R2C = 1, NSB_Z_FUSED = 2 };
+
+struct FftOps {
+    int N;
+    int strided_T;                 // kz columns per strided tile
+    int z_pairs_per_cta;           // G
+    int (*setup)(void);            // opt-in to large dynamic shared memory; returns cudaError_t
+    // one c2c pass over `nfields` fields; grid = (ceil(nzv/T), n_outer_eff, nfields)
+    int (*strided)(int dir, const StridedArgs* a, int n_outer_eff, int nfields, cudaStream_t s);
+    // z kernels; grid_x CTAs loop over the row pairs
+    int (*z)(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s);
+    // resident CTAs per SM of a z kernel (for sizing the persistent grid)
+    int (*z_occupancy)(int which);
+};
+
+const FftOps* nsb_get_fft_ops(int N);

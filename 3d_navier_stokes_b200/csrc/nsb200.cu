@@ -1,0 +1,707 @@
+// libnsb200.so: context, transform plumbing and the C ABI declared in include/nsb200.h.
+//
+// Device layout (DESIGN.md "data layout"): every vector field is planar, component-major,
+//   F[c][kx_local][ky][nzp]  complex128, kz fastest, rows padded to nzp = roundup(Nz/2+1, 8)
+// so every 1-D pass reads and writes whole 128-byte lines.  State: U (u_hat), TMP (RK stage input),
+// ACC (running sum of B_i k_i); workspace W (6 fields: u and w = i k x u through the inverse
+// transform, u x w back through the forward one) and, with more than one rank, R (6 fields, the
+// receive side of the slab all-to-all).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nsb200.h"
+#include "fft_ops.h"
+#include "pointwise_kernels.cuh"
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                        std::to_string(__LINE__) + ")");                                              \
+    } while (0)
+#define CKI(call)                                                                                     \
+    do {                                                                                              \
+        int e_ = (call);                                                                              \
+        if (e_ != 0)                                                                                  \
+            return fail(std::string(#call) + " failed: " + cudaGetErrorString((cudaError_t)e_) + " (" __FILE__ ":" + \
+                        std::to_string(__LINE__) + ")");                                              \
+    } while (0)
+#define CKR(call)              \
+    do {                       \
+        int r_ = (call);       \
+        if (r_ != 0) return r_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------ NCCL (resolved at run time)
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+#define NSB_SYM(field, name)                                                  \
+    *(void**)(&g_nccl.field) = dlsym(lib, name);                              \
+    if (!g_nccl.field) return fail(std::string("NCCL symbol missing: ") + name);
+    NSB_SYM(GetUniqueId, "ncclGetUniqueId")
+    NSB_SYM(CommInitRank, "ncclCommInitRank")
+    NSB_SYM(CommDestroy, "ncclCommDestroy")
+    NSB_SYM(Send, "ncclSend")
+    NSB_SYM(Recv, "ncclRecv")
+    NSB_SYM(AllReduce, "ncclAllReduce")
+    NSB_SYM(GroupStart, "ncclGroupStart")
+    NSB_SYM(GroupEnd, "ncclGroupEnd")
+    NSB_SYM(GetErrorString, "ncclGetErrorString")
+#undef NSB_SYM
+    g_nccl.lib = lib;
+    return 0;
+}
+#define CKN(call)                                                                                           \
+    do {                                                                                                    \
+        ncclResult_t r_ = (call);                                                                           \
+        if (r_ != ncclSuccess)                                                                              \
+            return fail(std::string(#call) + " failed: " + g_nccl.GetErrorString(r_) + " (" __FILE__ ":" + \
+                        std::to_string(__LINE__) + ")");                                                    \
+    } while (0)
+
+// ------------------------------------------------------------------------------ size dispatch
+#define NSB_DECL_OPS(n) extern const FftOps nsb_fft_ops_##n;
+NSB_DECL_OPS(16) NSB_DECL_OPS(32) NSB_DECL_OPS(64) NSB_DECL_OPS(128) NSB_DECL_OPS(256) NSB_DECL_OPS(512) NSB_DECL_OPS(1024)
+const FftOps* nsb_get_fft_ops(int N) {
+    switch (N) {
+        case 16: return &nsb_fft_ops_16;
+        case 32: return &nsb_fft_ops_32;
+        case 64: return &nsb_fft_ops_64;
+        case 128: return &nsb_fft_ops_128;
+        case 256: return &nsb_fft_ops_256;
+        case 512: return &nsb_fft_ops_512;
+        case 1024: return &nsb_fft_ops_1024;
+        default: return nullptr;
+    }
+}
+
+// ------------------------------------------------------------------------------ context
+struct nsb200_ctx {
+    int N = 0, nzf = 0, nzp = 0;
+    int device = 0, rank = 0, nranks = 1;
+    int nx_loc = 0, x_start = 0, ny_loc = 0;
+    double nu = 0, visc_pow = 1;
+    int system = 0, dealias = 1, kmax2 = 0;
+    size_t field_elems = 0;        // complex elements per planar local field
+    cplx* slab = nullptr;          // one allocation for all fields
+    cplx *U[3], *TMP[3], *ACC[3], *W[6], *R[6];
+    cplx* tw = nullptr;
+    double* meas_partial = nullptr;
+    double* meas_dev = nullptr;
+    double* meas_host = nullptr;   // pinned
+    double* spect_dev = nullptr;
+    int meas_grid = 0;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_field;   // per-field compute->comm and comm->compute fences
+    std::vector<cudaEvent_t> ev_comm;
+    const FftOps* ops = nullptr;
+    ncclComm_t comm = nullptr;
+    int sm_count = 0;
+    int zgrid[3] = {0, 0, 0};
+    long launches = 0;
+    size_t bytes = 0;
+    Geom geom() const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.x_start = x_start; return g; }
+    long long nrows() const { return (long long)nx_loc * N; }
+    int row_grid() const { long long r = nrows(); long long cap = (long long)sm_count * 32; return (int)(r < cap ? r : cap); }
+};
+
+static int set_device(nsb200_ctx* h) { CK(cudaSetDevice(h->device)); return 0; }
+
+// ------------------------------------------------------------------------------ transform plumbing
+// One strided c2c pass.  axis 'y': Fourier slab [kx_loc][ky][kz], outer = kx_loc.  axis 'x': after the slab
+// exchange [kx][y_loc][kz], outer = y_loc.  `exch` selects the all-to-all block layout on the output
+// ('o', inverse y pass) or input ('i', forward y pass) side: element n of the transformed axis lives
+// at (n / ny_loc) * block + (n % ny_loc) * nzp, i.e. one contiguous block per destination rank.
+static int run_pass(nsb200_ctx* h, char axis, int dir, int nfields, cplx* const* src, cplx* const* dst, char exch,
+                    int field0 = 0, int field_cnt = -1) {
+    StridedArgs a;
+    memset(&a, 0, sizeof a);
+    if (field_cnt < 0) field_cnt = nfields;
+    for (int f = 0; f < field_cnt; ++f) { a.src[f] = src[field0 + f]; a.dst[f] = dst[field0 + f]; }
+    a.tw = h->tw;
+    a.nzv = h->nzf;
+    a.outer_lo = a.outer_hi = 0;
+    a.in_zero_lo = a.in_zero_hi = h->N;
+    a.out_skip_lo = a.out_skip_hi = h->N;
+    const long long nzp = h->nzp;
+    int n_outer;
+    a.in_shift = a.out_shift = 30; a.in_mask = a.out_mask = 0x3fffffff; a.in_s1 = a.out_s1 = 0;
+    if (axis == 'y') {
+        n_outer = h->nx_loc;
+        a.in_so = a.out_so = (long long)h->N * nzp;
+        a.in_s2 = a.out_s2 = nzp;
+        if (h->nranks > 1 && exch != 'n') {
+            int sh = 0;
+            while ((1 << sh) < h->ny_loc) ++sh;
+            const long long block = (long long)h->nx_loc * h->ny_loc * nzp;
+            if (exch == 'o') { a.out_shift = sh; a.out_mask = h->ny_loc - 1; a.out_s1 = block; a.out_so = (long long)h->ny_loc * nzp; }
+            else { a.in_shift = sh; a.in_mask = h->ny_loc - 1; a.in_s1 = block; a.in_so = (long long)h->ny_loc * nzp; }
+        }
+    } else {
+        n_outer = h->ny_loc;
+        a.in_so = a.out_so = nzp;
+        a.in_s2 = a.out_s2 = (long long)h->ny_loc * nzp;
+    }
+    CKI(h->ops->strided(dir, &a, n_outer, field_cnt, h->stream));
+    h->launches++;
+    return 0;
+}
+
+static int run_z(nsb200_ctx* h, int which, int nfields, cplx* const* f) {
+    ZArgs a;
+    memset(&a, 0, sizeof a);
+    for (int i = 0; i < (which == NSB_Z_FUSED ? 6 : nfields); ++i) a.f[i] = f[i];
+    a.tw = h->tw;
+    a.rs = h->nzp;
+    a.npairs = (long long)h->N * h->ny_loc / 2;
+    a.kz_in = h->nzf;
+    a.kz_out = h->nzf;
+    long long want = (a.npairs + h->ops->z_pairs_per_cta - 1) / h->ops->z_pairs_per_cta;
+    int grid = (int)(want < h->zgrid[which] ? want : h->zgrid[which]);
+    CKI(h->ops->z(which, &a, nfields, grid, h->stream));
+    h->launches++;
+    return 0;
+}
+
+// Slab all-to-all of `cnt` fields starting at field0: block s of every field goes to rank s.
+static int exchange(nsb200_ctx* h, cplx* const* send, cplx* const* recv, int field0, int cnt, cudaStream_t s) {
+    const size_t block = (size_t)h->nx_loc * h->ny_loc * h->nzp;   // complex elements
+    CKN(g_nccl.GroupStart());
+    for (int f = field0; f < field0 + cnt; ++f)
+        for (int p = 0; p < h->nranks; ++p) {
+            CKN(g_nccl.Send(send[f] + p * block, 2 * block, ncclDouble, p, h->comm, s));
+            CKN(g_nccl.Recv(recv[f] + p * block, 2 * block, ncclDouble, p, h->comm, s));
+        }
+    CKN(g_nccl.GroupEnd());
+    return 0;
+}
+
+// NonlinearRHSBatch up to (not including) normalise/project/dealias: raw (u x w)^ of `in` left in R[0..2].
+// solver.c:637-683.  Multi-rank: per-field pipelining of y pass -> all-to-all -> x pass over two streams.
+static int rhs_raw(nsb200_ctx* h, cplx* const* in) {
+    const int rg = h->row_grid();
+    CurlArgs ca;
+    for (int d = 0; d < 3; ++d) { ca.u[d] = in[d]; ca.w[d] = h->R[3 + d]; }
+    ca.g = h->geom();
+    k_curl<<<rg, 128, 0, h->stream>>>(ca);
+    CK(cudaGetLastError());
+    h->launches++;
+    cplx* src[6] = {in[0], in[1], in[2], h->R[3], h->R[4], h->R[5]};
+    if (h->nranks == 1) {
+        CKR(run_pass(h, 'y', INV, 6, src, h->W, 'n'));
+        CKR(run_pass(h, 'x', INV, 6, h->W, h->W, 'n'));
+        CKR(run_z(h, NSB_Z_FUSED, 3, h->W));
+        CKR(run_pass(h, 'x', FWD, 3, h->W, h->W, 'n'));
+        CKR(run_pass(h, 'y', FWD, 3, h->W, h->R, 'n'));   // R aliases W when nranks == 1
+        return 0;
+    }
+    // inverse: y pass (field f) | exchange (field f) | x pass (field f), pipelined across fields
+    for (int f = 0; f < 6; ++f) {
+        CKR(run_pass(h, 'y', INV, 6, src, h->W, 'o', f, 1));
+        CK(cudaEventRecord(h->ev_field[f], h->stream));
+        CK(cudaStreamWaitEvent(h->comm_stream, h->ev_field[f], 0));
+        CKR(exchange(h, h->W, h->R, f, 1, h->comm_stream));
+        CK(cudaEventRecord(h->ev_comm[f], h->comm_stream));
+    }
+    for (int f = 0; f < 6; ++f) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_comm[f], 0));
+        CKR(run_pass(h, 'x', INV, 6, h->R, h->R, 'n', f, 1));
+    }
+    CKR(run_z(h, NSB_Z_FUSED, 3, h->R));
+    for (int f = 0; f < 3; ++f) {
+        CKR(run_pass(h, 'x', FWD, 3, h->R, h->R, 'n', f, 1));
+        CK(cudaEventRecord(h->ev_field[f], h->stream));
+        CK(cudaStreamWaitEvent(h->comm_stream, h->ev_field[f], 0));
+        CKR(exchange(h, h->R, h->W, f, 1, h->comm_stream));
+        CK(cudaEventRecord(h->ev_comm[f], h->comm_stream));
+    }
+    // the forward y pass writes R[0..2] (natural order): all exchanges out of R must be complete
+    for (int f = 0; f < 3; ++f) CK(cudaStreamWaitEvent(h->stream, h->ev_comm[f], 0));
+    CKR(run_pass(h, 'y', FWD, 3, h->W, h->R, 'i'));
+    return 0;
+}
+
+static int rk_stage(nsb200_ctx* h, int stage, double dt) {
+    RkArgs a;
+    memset(&a, 0, sizeof a);
+    for (int d = 0; d < 3; ++d) { a.c[d] = h->R[d]; a.u[d] = h->U[d]; a.tmp[d] = h->TMP[d]; a.acc[d] = h->ACC[d]; a.uout[d] = h->U[d]; }
+    a.g = h->geom();
+    a.stage = stage;
+    a.dealias = h->dealias;
+    a.kmax2 = h->kmax2;
+    a.euler = (h->system == NSB200_SYSTEM_EULER);
+    a.hyper2 = (h->visc_pow == 2.0);
+    a.dt = dt; a.nu = h->nu; a.visc_pow = h->visc_pow;
+    const double n3 = (double)h->N * (double)h->N * (double)h->N;
+    a.norm = 1.0 / (n3 * n3);   // 1/pow(Nx*Ny*Nz, 2.0), solver.c:631 (exact for powers of two)
+    k_rk_stage<<<h->row_grid(), 128, 0, h->stream>>>(a);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+static int step(nsb200_ctx* h, double dt) {
+    CKR(rhs_raw(h, h->U));   CKR(rk_stage(h, 0, dt));   // solver.c:522-536
+    CKR(rhs_raw(h, h->TMP)); CKR(rk_stage(h, 1, dt));   // :538-552
+    CKR(rhs_raw(h, h->TMP)); CKR(rk_stage(h, 2, dt));   // :554-568
+    CKR(rhs_raw(h, h->TMP)); CKR(rk_stage(h, 3, dt));   // :570-607
+    return 0;
+}
+
+// forward / inverse 3-D transforms of 3 planar fields held in W (single rank), real <-> half complex in place
+static int fft3_r2c_inplace(nsb200_ctx* h) {
+    CKR(run_z(h, NSB_Z_R2C, 3, h->W));
+    CKR(run_pass(h, 'x', FWD, 3, h->W, h->W, 'n'));
+    CKR(run_pass(h, 'y', FWD, 3, h->W, h->W, 'n'));
+    return 0;
+}
+static int fft3_c2r_inplace(nsb200_ctx* h) {
+    CKR(run_pass(h, 'y', INV, 3, h->W, h->W, 'n'));
+    CKR(run_pass(h, 'x', INV, 3, h->W, h->W, 'n'));
+    CKR(run_z(h, NSB_Z_C2R, 3, h->W));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* nsb200_version(void) { return "nsb200 0.1 sm_100a"; }
+const char* nsb200_last_error(void) { return g_err.c_str(); }
+
+int nsb200_get_nccl_unique_id(void* out128) {
+    CKR(load_nccl());
+    ncclUniqueId id;
+    CKN(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+int nsb200_destroy(nsb200_ctx* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    if (h->comm) g_nccl.CommDestroy(h->comm);
+    cudaFree(h->slab); cudaFree(h->tw); cudaFree(h->meas_partial); cudaFree(h->meas_dev); cudaFree(h->spect_dev);
+    cudaFree(h->flush_buf);
+    if (h->meas_host) cudaFreeHost(h->meas_host);
+    for (auto e : h->ev_field) cudaEventDestroy(e);
+    for (auto e : h->ev_comm) cudaEventDestroy(e);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, double visc_pow, int system,
+                  int dealias_mode, int rank, int n_ranks, const void* nccl_unique_id) {
+    if (!out || !N) return fail("nsb200_create: null argument");
+    *out = nullptr;
+    if (N[0] != N[1] || N[1] != N[2]) return fail("nsb200_create: only cubic grids are supported (Nx == Ny == Nz)");
+    const FftOps* ops = nsb_get_fft_ops((int)N[0]);
+    if (!ops) return fail("nsb200_create: N must be a power of two in [16, 1024]");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail("nsb200_create: bad rank / n_ranks");
+    if (N[0] % n_ranks != 0 || (N[0] / n_ranks) % 2 != 0) return fail("nsb200_create: n_ranks must divide N with an even slab thickness");
+    if (n_ranks > 1 && !nccl_unique_id) return fail("nsb200_create: nccl_unique_id required when n_ranks > 1");
+    if (system != NSB200_SYSTEM_NAVIER && system != NSB200_SYSTEM_EULER) return fail("nsb200_create: bad system");
+    if (dealias_mode != NSB200_DEALIAS_NONE && dealias_mode != NSB200_DEALIAS_23) return fail("nsb200_create: bad dealias_mode");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("nsb200_create: no CUDA device available (libnsb200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("nsb200_create: bad device ordinal");
+    nsb200_ctx* h = new nsb200_ctx();
+    h->N = (int)N[0]; h->nzf = h->N / 2 + 1; h->nzp = (h->nzf + 7) / 8 * 8;
+    h->device = device; h->rank = rank; h->nranks = n_ranks;
+    h->nx_loc = h->N / n_ranks; h->x_start = rank * h->nx_loc; h->ny_loc = h->N / n_ranks;
+    h->nu = nu; h->visc_pow = visc_pow; h->system = system; h->dealias = dealias_mode;
+    const int kmax = h->N / 3;   // integer division, solver.c:1732
+    h->kmax2 = kmax * kmax;
+    h->ops = ops;
+    h->field_elems = (size_t)h->nx_loc * h->N * h->nzp;
+#define CKC(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            fail(std::string(#call) + " failed: " + cudaGetErrorString(e_));                         \
+            nsb200_destroy(h);                                                                       \
+            return 1;                                                                                \
+        }                                                                                            \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { nsb200_destroy(h); return fail("nsb200_create: requires an sm_100a (Blackwell B200) device"); }
+    h->sm_count = prop.multiProcessorCount;
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&h->ev0));
+    CKC(cudaEventCreate(&h->ev1));
+    for (int i = 0; i < 6; ++i) {
+        cudaEvent_t e;
+        CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_field.push_back(e);
+        CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_comm.push_back(e);
+    }
+    const int nfields = (n_ranks > 1) ? 21 : 15;
+    h->bytes = (size_t)nfields * h->field_elems * sizeof(cplx);
+    CKC(cudaMalloc(&h->slab, h->bytes));
+    CKC(cudaMemsetAsync(h->slab, 0, h->bytes, h->stream));
+    for (int d = 0; d < 3; ++d) {
+        h->U[d] = h->slab + (size_t)d * h->field_elems;
+        h->TMP[d] = h->slab + (size_t)(3 + d) * h->field_elems;
+        h->ACC[d] = h->slab + (size_t)(6 + d) * h->field_elems;
+    }
+    for (int f = 0; f < 6; ++f) {
+        h->W[f] = h->slab + (size_t)(9 + f) * h->field_elems;
+        h->R[f] = (n_ranks > 1) ? h->slab + (size_t)(15 + f) * h->field_elems : h->W[f];
+    }
+    // twiddles exp(-2 pi i m / N), rounded from long double
+    {
+        std::vector<cplx> tw(h->N);
+        for (int m = 0; m < h->N; ++m) {
+            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)h->N;
+            tw[m] = mk((double)cosl(ang), (double)sinl(ang));
+        }
+        CKC(cudaMalloc(&h->tw, sizeof(cplx) * h->N));
+        CKC(cudaMemcpyAsync(h->tw, tw.data(), sizeof(cplx) * h->N, cudaMemcpyHostToDevice, h->stream));
+        CKC(cudaStreamSynchronize(h->stream));
+        h->bytes += sizeof(cplx) * h->N;
+    }
+    h->meas_grid = (int)std::min<long long>(h->nrows(), (long long)h->sm_count * 8);
+    CKC(cudaMalloc(&h->meas_partial, sizeof(double) * NSB_NMEAS * h->meas_grid));
+    CKC(cudaMalloc(&h->meas_dev, sizeof(double) * NSB_NMEAS));
+    CKC(cudaMalloc(&h->spect_dev, sizeof(double) * 2 * 2048));
+    CKC(cudaMallocHost(&h->meas_host, sizeof(double) * 2 * 2048));
+    {
+        int e = ops->setup();
+        if (e != 0) { fail(std::string("kernel attribute setup failed: ") + cudaGetErrorString((cudaError_t)e)); nsb200_destroy(h); return 1; }
+        for (int w = 0; w < 3; ++w) {
+            int occ = ops->z_occupancy(w);
+            if (occ < 1) { fail("z kernel does not fit on an SM"); nsb200_destroy(h); return 1; }
+            h->zgrid[w] = occ * h->sm_count;
+        }
+    }
+    if (n_ranks > 1) {
+        if (load_nccl() != 0) { nsb200_destroy(h); return 1; }
+        ncclUniqueId id;
+        memcpy(&id, nccl_unique_id, sizeof id);
+        ncclResult_t r = g_nccl.CommInitRank(&h->comm, n_ranks, id, rank);
+        if (r != ncclSuccess) { fail(std::string("ncclCommInitRank failed: ") + g_nccl.GetErrorString(r)); nsb200_destroy(h); return 1; }
+    }
+    CKC(cudaStreamSynchronize(h->stream));
+#undef CKC
+    *out = h;
+    return 0;
+}
+
+int nsb200_local_slab(nsb200_ctx* h, long* local_nx, long* local_nx_start) {
+    if (!h) return fail("null handle");
+    if (local_nx) *local_nx = h->nx_loc;
+    if (local_nx_start) *local_nx_start = h->x_start;
+    return 0;
+}
+long nsb200_local_fourier_elems(nsb200_ctx* h) { return h ? 3L * h->nx_loc * h->N * h->nzf : 0; }
+long nsb200_launch_count(nsb200_ctx* h) { return h ? h->launches : 0; }
+long nsb200_device_bytes(nsb200_ctx* h) { return h ? (long)h->bytes : 0; }
+
+static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
+    const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
+    cplx* stage = h->W[0];   // W is one contiguous 6-field buffer >= the 3-field host layout
+    CK(cudaMemcpyAsync(stage, host, n * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    k_aos_to_planar<<<h->row_grid(), 128, 0, h->stream>>>(stage, dst[0], dst[1], dst[2], h->geom(), h->nrows());
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+static int download_from(nsb200_ctx* h, double* host, cplx* const* src) {
+    const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
+    cplx* stage = h->W[0];
+    k_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, src[0], src[1], src[2], h->geom(), h->nrows());
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaMemcpyAsync(host, stage, n * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int nsb200_upload_uhat(nsb200_ctx* h, const double* u_hat_host) {
+    if (!h || !u_hat_host) return fail("nsb200_upload_uhat: null argument");
+    CKR(set_device(h));
+    CKR(upload_to(h, u_hat_host, h->U));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int nsb200_download_uhat(nsb200_ctx* h, double* u_hat_host) {
+    if (!h || !u_hat_host) return fail("nsb200_download_uhat: null argument");
+    CKR(set_device(h));
+    return download_from(h, u_hat_host, h->U);
+}
+
+int nsb200_rk4_step(nsb200_ctx* h, double dt) {
+    if (!h) return fail("nsb200_rk4_step: null handle");
+    CKR(set_device(h));
+    return step(h, dt);
+}
+int nsb200_rk4_steps(nsb200_ctx* h, double dt, int n_steps) {
+    if (!h) return fail("nsb200_rk4_steps: null handle");
+    CKR(set_device(h));
+    for (int i = 0; i < n_steps; ++i) CKR(step(h, dt));
+    return 0;
+}
+
+int nsb200_nonlinear_rhs(nsb200_ctx* h, const double* u_hat_in, double* dw_hat_dt_out) {
+    if (!h || !u_hat_in || !dw_hat_dt_out) return fail("nsb200_nonlinear_rhs: null argument");
+    CKR(set_device(h));
+    CKR(upload_to(h, u_hat_in, h->TMP));
+    CKR(rhs_raw(h, h->TMP));
+    CKR(rk_stage(h, 4, 0.0));   // normalise + project + dealias -> ACC
+    return download_from(h, dw_hat_dt_out, h->ACC);
+}
+
+int nsb200_apply_dealiasing(nsb200_ctx* h, double* array_host, int array_dim) {
+    if (!h || !array_host) return fail("nsb200_apply_dealiasing: null argument");
+    if (array_dim < 1 || array_dim > 3) return fail("nsb200_apply_dealiasing: array_dim must be 1..3");
+    CKR(set_device(h));
+    const size_t n = (size_t)array_dim * h->nx_loc * h->N * h->nzf;
+    cplx* stage = h->W[0];
+    CK(cudaMemcpyAsync(stage, array_host, n * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    if (h->dealias == NSB200_DEALIAS_23) {
+        k_dealias_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, array_dim, h->geom(), h->kmax2, h->nrows());
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    CK(cudaMemcpyAsync(array_host, stage, n * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int measure_device(nsb200_ctx* h) {
+    MeasArgs a;
+    for (int d = 0; d < 3; ++d) a.u[d] = h->U[d];
+    a.partial = h->meas_partial;
+    a.g = h->geom();
+    a.nu = h->nu; a.visc_pow = h->visc_pow; a.hyper2 = (h->visc_pow == 2.0);
+    k_measure<<<h->meas_grid, 256, 0, h->stream>>>(a);
+    CK(cudaGetLastError());
+    k_measure_final<<<1, 32, 0, h->stream>>>(h->meas_partial, h->meas_grid, h->meas_dev);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    if (h->nranks > 1) CKN(g_nccl.AllReduce(h->meas_dev, h->meas_dev, NSB_NMEAS, ncclDouble, ncclSum, h->comm, h->stream));
+    return 0;
+}
+
+int nsb200_measure(nsb200_ctx* h, double out[NSB200_NMEASURE]) {
+    if (!h || !out) return fail("nsb200_measure: null argument");
+    CKR(set_device(h));
+    CKR(measure_device(h));
+    CK(cudaMemcpyAsync(h->meas_host, h->meas_dev, sizeof(double) * NSB_NMEAS, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->meas_host, sizeof(double) * NSB_NMEAS);
+    return 0;
+}
+
+int nsb200_assemble_measurables(const double p[NSB200_NMEASURE], const long N[3], int literal, double v[5]) {
+    if (!p || !N || !v) return fail("nsb200_assemble_measurables: null argument");
+    const double n3 = (double)N[0] * (double)N[1] * (double)N[2];
+    const double norm_fac = 0.5 / (n3 * n3);                       // solver.c:1154
+    const double const_fac = 8.0 * pow(M_PI, 3.0);                 // solver.c:1155
+    const double c = const_fac * norm_fac;
+    auto tot = [&](int e, int i) {
+        const double edge = p[e] + p[e + 1] + p[e + 2];
+        if (literal) return edge + 2.0 * p[i] + p[i + 1] + p[i + 2];   // solver.c:1232,1233,1235
+        return edge + 2.0 * (p[i] + p[i + 1] + p[i + 2]);
+    };
+    v[0] = tot(0, 3) * c;          // tot_energy   (solver.c:1274)
+    v[1] = tot(6, 9) * c;          // tot_enstr    (:1271)
+    v[2] = tot(12, 15) * c;        // tot_palin    (:1272)
+    v[3] = p[18] * c;              // tot_heli     (:1273)
+    v[4] = p[19] * 2.0 * c;        // enrg_diss    (:1270)
+    return 0;
+}
+
+int nsb200_fft_r2c(nsb200_ctx* h, const double* real_in, double* cplx_out) {
+    if (!h || !real_in || !cplx_out) return fail("nsb200_fft_r2c: null argument");
+    if (h->nranks != 1) return fail("nsb200_fft_r2c: single rank only");
+    CKR(set_device(h));
+    const size_t nreal = (size_t)3 * h->N * h->N * (h->N + 2);
+    double* stage = reinterpret_cast<double*>(h->W[3]);
+    CK(cudaMemcpyAsync(stage, real_in, nreal * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_real_aos_to_planar<<<h->row_grid(), 128, 0, h->stream>>>(stage, (double*)h->W[0], (double*)h->W[1], (double*)h->W[2], h->geom(), h->nrows());
+    CK(cudaGetLastError());
+    h->launches++;
+    CKR(fft3_r2c_inplace(h));
+    k_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(h->W[3], h->W[0], h->W[1], h->W[2], h->geom(), h->nrows());
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaMemcpyAsync(cplx_out, h->W[3], (size_t)3 * h->N * h->N * h->nzf * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int nsb200_fft_c2r(nsb200_ctx* h, const double* cplx_in, double* real_out) {
+    if (!h || !cplx_in || !real_out) return fail("nsb200_fft_c2r: null argument");
+    if (h->nranks != 1) return fail("nsb200_fft_c2r: single rank only");
+    CKR(set_device(h));
+    CK(cudaMemcpyAsync(h->W[3], cplx_in, (size_t)3 * h->N * h->N * h->nzf * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    k_aos_to_planar<<<h->row_grid(), 128, 0, h->stream>>>(h->W[3], h->W[0], h->W[1], h->W[2], h->geom(), h->nrows());
+    CK(cudaGetLastError());
+    h->launches++;
+    CKR(fft3_c2r_inplace(h));
+    double* stage = reinterpret_cast<double*>(h->W[3]);
+    k_real_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, (double*)h->W[0], (double*)h->W[1], (double*)h->W[2], h->geom(), h->nrows());
+    CK(cudaGetLastError());
+    h->launches++;
+    const size_t nreal = (size_t)3 * h->N * h->N * (h->N + 2);
+    CK(cudaMemcpyAsync(real_out, stage, nreal * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int nsb200_initial_condition(nsb200_ctx* h, const char* name, unsigned long long seed, double kp, double energy) {
+    if (!h || !name) return fail("nsb200_initial_condition: null argument");
+    CKR(set_device(h));
+    const int rg = h->row_grid();
+    if (!strcmp(name, "TAYLOR_GREEN") || !strcmp(name, "SHAPIRO")) {
+        if (h->nranks != 1) return fail("nsb200_initial_condition: TAYLOR_GREEN / SHAPIRO are generated on a single rank; upload the slab instead");
+        IcArgs a;
+        for (int d = 0; d < 3; ++d) a.r[d] = reinterpret_cast<double*>(h->W[d]);
+        a.g = h->geom();
+        a.kind = !strcmp(name, "SHAPIRO");
+        a.nu = h->nu;
+        k_ic_real<<<rg, 128, 0, h->stream>>>(a);
+        CK(cudaGetLastError());
+        h->launches++;
+        CKR(fft3_r2c_inplace(h));                                   // solver.c:1573 / :1599
+        for (int d = 0; d < 3; ++d)
+            CK(cudaMemcpyAsync(h->U[d], h->W[d], h->field_elems * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
+    } else if (!strcmp(name, "RANDOM_PHASE")) {
+        RandArgs a;
+        for (int d = 0; d < 3; ++d) a.u[d] = h->U[d];
+        a.g = h->geom(); a.seed = seed; a.kp = kp; a.kmax2 = h->kmax2;
+        k_ic_random_phase<<<rg, 128, 0, h->stream>>>(a);
+        CK(cudaGetLastError());
+        h->launches++;
+    } else {
+        return fail(std::string("nsb200_initial_condition: unknown initial condition '") + name + "'");
+    }
+    if (h->dealias == NSB200_DEALIAS_23) {                          // solver.c:1630
+        k_dealias_planar<<<rg, 128, 0, h->stream>>>(h->U[0], h->U[1], h->U[2], h->geom(), h->kmax2);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    if (!strcmp(name, "RANDOM_PHASE") && energy > 0.0) {
+        double p[NSB_NMEAS], v[5];
+        CKR(nsb200_measure(h, p));
+        const long NN[3] = {h->N, h->N, h->N};
+        nsb200_assemble_measurables(p, NN, 0, v);
+        if (!(v[0] > 0.0)) return fail("nsb200_initial_condition: random field has zero energy");
+        k_scale_planar<<<rg, 128, 0, h->stream>>>(h->U[0], h->U[1], h->U[2], h->geom(), sqrt(energy / v[0]));
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int nsb200_host_register(void* ptr, unsigned long long bytes) {
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+int nsb200_host_unregister(void* ptr) {
+    CK(cudaHostUnregister(ptr));
+    return 0;
+}
+
+int nsb200_spectra(nsb200_ctx* h, double* enrg_spect, double* enst_spect, int n_spect) {
+    if (!h) return fail("nsb200_spectra: null handle");
+    if (n_spect < 1 || n_spect > 2048) return fail("nsb200_spectra: bad n_spect");
+    CKR(set_device(h));
+    CK(cudaMemsetAsync(h->spect_dev, 0, sizeof(double) * 2 * 2048, h->stream));
+    SpectArgs a;
+    for (int d = 0; d < 3; ++d) a.u[d] = h->U[d];
+    a.g = h->geom();
+    a.enrg = h->spect_dev; a.enst = h->spect_dev + 2048; a.n_spect = n_spect;
+    const double n3 = (double)h->N * (double)h->N * (double)h->N;
+    a.fac = 8.0 * pow(M_PI, 3.0) * (0.5 / (n3 * n3));
+    k_spectra<<<h->meas_grid, 256, sizeof(double) * 2 * n_spect, h->stream>>>(a);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (h->nranks > 1) CKN(g_nccl.AllReduce(h->spect_dev, h->spect_dev, 2 * 2048, ncclDouble, ncclSum, h->comm, h->stream));
+    CK(cudaMemcpyAsync(h->meas_host, h->spect_dev, sizeof(double) * 2 * 2048, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (enrg_spect) memcpy(enrg_spect, h->meas_host, sizeof(double) * n_spect);
+    if (enst_spect) memcpy(enst_spect, h->meas_host + 2048, sizeof(double) * n_spect);
+    return 0;
+}
+
+int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_ms) {
+    if (!h || !elapsed_ms) return fail("nsb200_time_op: null argument");
+    if (iters < 1) return fail("nsb200_time_op: iters must be >= 1");
+    CKR(set_device(h));
+    if (op == NSB200_OP_L2_FLUSH && !h->flush_buf) {
+        h->flush_bytes = (size_t)256 << 20;
+        CK(cudaMalloc(&h->flush_buf, h->flush_bytes));
+        h->bytes += h->flush_bytes;
+    }
+    if (op != NSB200_OP_RK4_STEP && op != NSB200_OP_L2_FLUSH && op != NSB200_OP_RK_POINTWISE && h->nranks != 1)
+        return fail("nsb200_time_op: single-pass timings are single rank only");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int it = 0; it < iters; ++it) {
+        switch (op) {
+            case NSB200_OP_RK4_STEP: CKR(step(h, dt)); break;
+            case NSB200_OP_FFT_C2R_R2C: CKR(fft3_c2r_inplace(h)); CKR(fft3_r2c_inplace(h)); break;
+            case NSB200_OP_PASS_Y: CKR(run_pass(h, 'y', INV, 3, h->W, h->W, 'n')); break;
+            case NSB200_OP_PASS_X: CKR(run_pass(h, 'x', INV, 3, h->W, h->W, 'n')); break;
+            case NSB200_OP_PASS_Z: CKR(run_z(h, NSB_Z_C2R, 3, h->W)); break;
+            case NSB200_OP_Z_FUSED: CKR(run_z(h, NSB_Z_FUSED, 3, h->W)); break;
+            case NSB200_OP_RK_POINTWISE: CKR(rk_stage(h, 1, dt)); break;
+            case NSB200_OP_L2_FLUSH: CK(cudaMemsetAsync(h->flush_buf, it & 0xff, h->flush_bytes, h->stream)); break;
+            default: return fail("nsb200_time_op: unknown op");
+        }
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *elapsed_ms = (double)ms;
+    return 0;
+}
+
+}  // extern "C"

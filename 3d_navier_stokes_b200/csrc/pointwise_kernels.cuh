@@ -1,0 +1,431 @@
+// Pointwise Fourier-space kernels of the hot path: layout conversion at the boundary, spectral curl
+// (solver.c:637-650), normalise + pressure projection + zero mode (solver.c:689-721), 2/3 dealiasing
+// (ApplyDealiasing, solver.c:1709-1756 with fix F2), RK4 stage updates and the Crank-Nicolson style
+// final update (RK4Step, solver.c:523-607), and the diagnostics sums (ComputeSystemMeasurables,
+// solver.c:1186-1263).  One CTA walks one (kx, ky) row of Nz/2+1 modes, so all accesses are
+// contiguous.  Arithmetic that the reference does pointwise is done with explicitly rounded
+// products/sums (no FMA contraction) in the reference's association order.
+#pragma once
+#include "fft_kernels.cuh"
+
+struct Geom {
+    int N;        // cubic grid size
+    int nzf;      // N/2 + 1
+    int nzp;      // row stride (complex elements) of the planar device fields
+    int nx_loc;   // local number of kx planes (slab)
+    int x_start;  // global index of the first local kx plane
+};
+
+NSB_HD int nsb_wavenum(int idx, int N) { return idx <= N / 2 ? idx : idx - N; }  // solver.c:1793,1807
+
+NSB_HD cplx rmul(double a, cplx z) { return mk(NSB_MUL(a, z.x), NSB_MUL(a, z.y)); }
+NSB_HD cplx caddr(cplx a, cplx b) { return mk(NSB_ADD(a.x, b.x), NSB_ADD(a.y, b.y)); }
+NSB_HD cplx csubr(cplx a, cplx b) { return mk(NSB_SUB(a.x, b.x), NSB_SUB(a.y, b.y)); }
+// I * z exactly as C99 complex multiplication by (0 + 1i) gives for finite z: (-im, re)
+NSB_HD cplx imul(cplx z) { return mk(-z.y, z.x); }
+
+// w = i k x u  (solver.c:645-647; same expression in ComputeSystemMeasurables :1199-1201)
+NSB_HD void curl_mode(int kx, int ky, int kz, cplx ux, cplx uy, cplx uz, cplx& wx, cplx& wy, cplx& wz) {
+    const double dkx = (double)kx, dky = (double)ky, dkz = (double)kz;
+    wx = imul(csubr(rmul(dky, uz), rmul(dkz, uy)));
+    wy = imul(csubr(rmul(dkz, ux), rmul(dkx, uz)));
+    wz = imul(csubr(rmul(dkx, uy), rmul(dky, ux)));
+}
+
+// ------------------------------------------------------------------------------ layout at the boundary
+// reference host layout: [kx][ky][kz][3] complex (solver.c:640-645)  <->  planar [c][kx][ky][nzp]
+__global__ void k_aos_to_planar(const cplx* __restrict__ aos, cplx* p0, cplx* p1, cplx* p2, Geom g, long long nrows) {
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const cplx* src = aos + row * g.nzf * 3;
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            p0[row * g.nzp + k] = src[3 * k + 0];
+            p1[row * g.nzp + k] = src[3 * k + 1];
+            p2[row * g.nzp + k] = src[3 * k + 2];
+        }
+    }
+}
+__global__ void k_planar_to_aos(cplx* __restrict__ aos, const cplx* p0, const cplx* p1, const cplx* p2, Geom g, long long nrows) {
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        cplx* dst = aos + row * g.nzf * 3;
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            dst[3 * k + 0] = p0[row * g.nzp + k];
+            dst[3 * k + 1] = p1[row * g.nzp + k];
+            dst[3 * k + 2] = p2[row * g.nzp + k];
+        }
+    }
+}
+// real fields: host [x][y][Nz+2][3] doubles (solver.c:667-672) <-> planar rows of 2*nzp doubles
+__global__ void k_real_aos_to_planar(const double* __restrict__ aos, double* p0, double* p1, double* p2, Geom g, long long nrows) {
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const double* src = aos + row * (g.N + 2) * 3;
+        for (int k = threadIdx.x; k < g.N; k += blockDim.x) {
+            p0[row * 2 * g.nzp + k] = src[3 * k + 0];
+            p1[row * 2 * g.nzp + k] = src[3 * k + 1];
+            p2[row * 2 * g.nzp + k] = src[3 * k + 2];
+        }
+    }
+}
+__global__ void k_real_planar_to_aos(double* __restrict__ aos, const double* p0, const double* p1, const double* p2, Geom g, long long nrows) {
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        double* dst = aos + row * (g.N + 2) * 3;
+        for (int k = threadIdx.x; k < g.N + 2; k += blockDim.x) {
+            const bool in = k < g.N;
+            dst[3 * k + 0] = in ? p0[row * 2 * g.nzp + k] : 0.0;
+            dst[3 * k + 1] = in ? p1[row * 2 * g.nzp + k] : 0.0;
+            dst[3 * k + 2] = in ? p2[row * 2 * g.nzp + k] : 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ spectral curl
+struct CurlArgs {
+    const cplx* u[3];
+    cplx* w[3];
+    Geom g;
+};
+__global__ void k_curl(const CurlArgs a) {
+    const Geom g = a.g;
+    const long long nrows = (long long)g.nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const long long base = row * g.nzp;
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            cplx wx, wy, wz;
+            curl_mode(kx, ky, k, a.u[0][base + k], a.u[1][base + k], a.u[2][base + k], wx, wy, wz);
+            a.w[0][base + k] = wx;
+            a.w[1][base + k] = wy;
+            a.w[2][base + k] = wz;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ projection + dealias + RK
+struct RkArgs {
+    const cplx* c[3];    // raw forward transform of u x w (unnormalised)
+    const cplx* u[3];    // u_hat at the start of the step
+    cplx* tmp[3];        // stage input written for the next stage
+    cplx* acc[3];        // running  B1 k1 + B2 k2 + B3 k3
+    cplx* uout[3];       // final update target (== u)
+    Geom g;
+    int stage;           // 0..3 = RK4 stages; 4 = RHS only (result to acc)
+    int dealias;         // 1 = 2/3 spherical cut with integer threshold
+    int kmax2;           // (N/3)^2
+    int euler;           // __EULER update (solver.c:585) instead of the viscous factor (:601)
+    int hyper2;          // visc_pow == 2 (pow(k_sqr, 2.0), solver.c:594)
+    double dt, nu, visc_pow, norm;
+};
+
+#define NSB_RK4_A21 0.5
+#define NSB_RK4_A32 0.5
+#define NSB_RK4_A43 1.0
+#define NSB_RK4_B1 (1.0 / 6.0)
+#define NSB_RK4_B2 (1.0 / 3.0)
+#define NSB_RK4_B3 (1.0 / 3.0)
+#define NSB_RK4_B4 (1.0 / 6.0)
+
+// solver.c:697-718 then :1732-1737 for one mode
+NSB_HD void project_mode(int kx, int ky, int kz, double norm, int dealias, int kmax2, cplx& c0, cplx& c1, cplx& c2) {
+    c0 = rmul(norm, c0); c1 = rmul(norm, c1); c2 = rmul(norm, c2);
+    const int k2 = kx * kx + ky * ky + kz * kz;
+    if (k2 != 0) {
+        const double k2inv = NSB_DIV(1.0, (double)k2);
+        const cplx kdot = caddr(caddr(rmul((double)kx, c0), rmul((double)ky, c1)), rmul((double)kz, c2));
+        c0 = csubr(c0, rmul(NSB_MUL((double)kx, k2inv), kdot));
+        c1 = csubr(c1, rmul(NSB_MUL((double)ky, k2inv), kdot));
+        c2 = csubr(c2, rmul(NSB_MUL((double)kz, k2inv), kdot));
+    } else {
+        c0 = c1 = c2 = mk(0.0, 0.0);
+    }
+    if (dealias && k2 > kmax2) c0 = c1 = c2 = mk(0.0, 0.0);
+}
+
+__global__ void k_rk_stage(const RkArgs a) {
+    const Geom g = a.g;
+    const long long nrows = (long long)g.nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const long long base = row * g.nzp;
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            const long long e = base + k;
+            cplx c[3] = {a.c[0][e], a.c[1][e], a.c[2][e]};
+            project_mode(kx, ky, k, a.norm, a.dealias, a.kmax2, c[0], c[1], c[2]);
+            if (a.stage == 4) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) a.acc[d][e] = c[d];
+                continue;
+            }
+            const double bcoef = a.stage == 0 ? NSB_RK4_B1 : a.stage == 1 ? NSB_RK4_B2 : a.stage == 2 ? NSB_RK4_B3 : NSB_RK4_B4;
+            if (a.stage < 3) {
+                const double acoef = NSB_MUL(a.dt, a.stage == 0 ? NSB_RK4_A21 : a.stage == 1 ? NSB_RK4_A32 : NSB_RK4_A43);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    cplx bk = rmul(bcoef, c[d]);
+                    if (a.euler) bk = rmul(a.dt, bk);
+                    a.acc[d][e] = (a.stage == 0) ? bk : caddr(a.acc[d][e], bk);
+                    a.tmp[d][e] = caddr(a.u[d][e], rmul(acoef, c[d]));
+                }
+            } else {
+                double f1 = 1.0, f2 = 1.0;
+                if (!a.euler) {
+                    const double k_sqr = (double)(kx * kx + ky * ky + k * k);
+                    double vis;
+                    if (a.hyper2) vis = NSB_MUL(k_sqr, k_sqr);
+                    else if (a.visc_pow == 1.0) vis = k_sqr;
+                    else vis = pow(k_sqr, a.visc_pow);
+                    const double D = NSB_MUL(a.dt, NSB_MUL(a.nu, vis));           // solver.c:594/597
+                    f1 = NSB_DIV(NSB_SUB(2.0, D), NSB_ADD(2.0, D));               // (2 - D)/(2 + D)
+                    f2 = NSB_DIV(NSB_MUL(2.0, a.dt), NSB_ADD(2.0, D));            // 2 dt/(2 + D)
+                }
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    cplx bk = rmul(bcoef, c[d]);
+                    if (a.euler) bk = rmul(a.dt, bk);
+                    const cplx comb = caddr(a.acc[d][e], bk);
+                    const cplx u = a.u[d][e];
+                    a.uout[d][e] = a.euler ? caddr(u, comb) : caddr(rmul(f1, u), rmul(f2, comb));
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ ApplyDealiasing on the host layout
+__global__ void k_dealias_aos(cplx* arr, int dim, Geom g, int kmax2, long long nrows) {
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            if (kx * kx + ky * ky + k * k > kmax2)
+                for (int l = 0; l < dim; ++l) arr[(row * g.nzf + k) * dim + l] = mk(0.0, 0.0);
+        }
+    }
+}
+__global__ void k_dealias_planar(cplx* p0, cplx* p1, cplx* p2, Geom g, int kmax2) {
+    const long long nrows = (long long)g.nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            if (kx * kx + ky * ky + k * k > kmax2) {
+                p0[row * g.nzp + k] = mk(0.0, 0.0);
+                p1[row * g.nzp + k] = mk(0.0, 0.0);
+                p2[row * g.nzp + k] = mk(0.0, 0.0);
+            }
+        }
+    }
+}
+__global__ void k_scale_planar(cplx* p0, cplx* p1, cplx* p2, Geom g, double s) {
+    const long long nrows = (long long)g.nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x)
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            const long long e = row * g.nzp + k;
+            p0[e] = cscale(p0[e], s); p1[e] = cscale(p1[e], s); p2[e] = cscale(p2[e], s);
+        }
+}
+
+// ------------------------------------------------------------------------------ diagnostics
+// 20 partial sums per call (see include/nsb200.h): per component x {kz edge, kz interior} of |u|^2,
+// |w|^2, |i k x w|^2, then sum wgt Re(u.w) and sum wgt nu |k|^(2p) |u|^2.  The host assembles both
+// the reference's literal values (precedence defect F4, solver.c:1232-1235) and the corrected ones.
+#define NSB_NMEAS 20
+struct MeasArgs {
+    const cplx* u[3];
+    double* partial;   // [gridDim.x][NSB_NMEAS]
+    Geom g;
+    double nu, visc_pow;
+    int hyper2;
+};
+NSB_HD double abs2(cplx z) { return NSB_ADD(NSB_MUL(z.x, z.x), NSB_MUL(z.y, z.y)); }
+
+__global__ void __launch_bounds__(256) k_measure(const MeasArgs a) {
+    const Geom g = a.g;
+    const long long nrows = (long long)g.nx_loc * g.N;
+    double acc[NSB_NMEAS];
+#pragma unroll
+    for (int m = 0; m < NSB_NMEAS; ++m) acc[m] = 0.0;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const long long base = row * g.nzp;
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            const cplx ux = a.u[0][base + k], uy = a.u[1][base + k], uz = a.u[2][base + k];
+            cplx wx, wy, wz, cx, cy, cz;
+            curl_mode(kx, ky, k, ux, uy, uz, wx, wy, wz);        // solver.c:1199-1201
+            curl_mode(kx, ky, k, wx, wy, wz, cx, cy, cz);        // solver.c:1206-1208
+            const double k_sqr = (double)(kx * kx + ky * ky + k * k);
+            double vis;
+            if (a.hyper2) vis = k_sqr * k_sqr;
+            else if (a.visc_pow == 1.0) vis = k_sqr;
+            else vis = pow(k_sqr, a.visc_pow);
+            const double pre = a.nu * vis;
+            const bool edge = (k == 0) || (k == g.nzf - 1);       // solver.c:1223
+            const int o = edge ? 0 : 3;
+            const double e0 = abs2(ux), e1 = abs2(uy), e2 = abs2(uz);
+            acc[0 + o] += e0; acc[1 + o] += e1; acc[2 + o] += e2;
+            acc[6 + o] += abs2(wx); acc[7 + o] += abs2(wy); acc[8 + o] += abs2(wz);
+            acc[12 + o] += abs2(cx); acc[13 + o] += abs2(cy); acc[14 + o] += abs2(cz);
+            // creal(u.w) with the plain (unconjugated) product, solver.c:1227
+            const double h = (ux.x * wx.x - ux.y * wx.y) + (uy.x * wy.x - uy.y * wy.y) + (uz.x * wz.x - uz.y * wz.y);
+            const double wgt = edge ? 1.0 : 2.0;
+            acc[18] += wgt * h;
+            acc[19] += wgt * pre * (e0 + e1 + e2);
+        }
+    }
+    __shared__ double red[8][NSB_NMEAS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int m = 0; m < NSB_NMEAS; ++m) {
+        double v = acc[m];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][m] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NSB_NMEAS) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+        a.partial[(long long)blockIdx.x * NSB_NMEAS + threadIdx.x] = v;
+    }
+}
+// fixed-order final sum: deterministic for a given grid
+__global__ void k_measure_final(const double* partial, int nblocks, double* out) {
+    const int m = threadIdx.x;
+    if (m < NSB_NMEAS) {
+        double v = 0.0;
+        for (int b = 0; b < nblocks; ++b) v += partial[(long long)b * NSB_NMEAS + m];
+        out[m] = v;
+    }
+}
+
+// shell spectra, binned at round(|k|) as solver.c:1242; shared-memory bins then one atomic per bin
+struct SpectArgs {
+    const cplx* u[3];
+    double* enrg;
+    double* enst;
+    Geom g;
+    int n_spect;
+    double fac;   // (2 pi)^3 * 0.5 / (N^3)^2, solver.c:1246
+};
+__global__ void __launch_bounds__(256) k_spectra(const SpectArgs a) {
+    extern __shared__ double nsb_bins[];
+    const Geom g = a.g;
+    for (int b = threadIdx.x; b < 2 * a.n_spect; b += blockDim.x) nsb_bins[b] = 0.0;
+    __syncthreads();
+    const long long nrows = (long long)g.nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const long long base = row * g.nzp;
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            const cplx ux = a.u[0][base + k], uy = a.u[1][base + k], uz = a.u[2][base + k];
+            cplx wx, wy, wz;
+            curl_mode(kx, ky, k, ux, uy, uz, wx, wy, wz);
+            const int bin = (int)round(sqrt((double)(kx * kx + ky * ky + k * k)));
+            if (bin >= a.n_spect) continue;
+            const double wgt = ((k == 0) || (k == g.nzf - 1)) ? 1.0 : 2.0;
+            atomicAdd(&nsb_bins[bin], wgt * a.fac * (abs2(ux) + abs2(uy) + abs2(uz)));
+            atomicAdd(&nsb_bins[a.n_spect + bin], wgt * a.fac * (abs2(wx) + abs2(wy) + abs2(wz)));
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < a.n_spect; b += blockDim.x) {
+        if (nsb_bins[b] != 0.0) atomicAdd(&a.enrg[b], nsb_bins[b]);
+        if (nsb_bins[a.n_spect + b] != 0.0) atomicAdd(&a.enst[b], nsb_bins[a.n_spect + b]);
+    }
+}
+
+// ------------------------------------------------------------------------------ initial conditions
+// Real-space Taylor-Green (solver.c:1565-1567) / Shapiro (solver.c:1591-1593 with fix F5) fill,
+// planar real rows of 2*nzp doubles; followed on the host side by the forward transform + dealias.
+struct IcArgs {
+    double* r[3];
+    Geom g;
+    int kind;   // 0 Taylor-Green, 1 Shapiro
+    double nu;
+};
+__global__ void k_ic_real(const IcArgs a) {
+    const Geom g = a.g;
+    const long long nrows = (long long)g.N * g.N;   // single-GPU real layout [x][y][z]
+    const double dx = 2.0 * 3.14159265358979323846 / (double)g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const double x = (double)i * dx, y = (double)j * dx;
+        for (int k = threadIdx.x; k < g.N; k += blockDim.x) {
+            const double z = (double)k * dx;
+            double u0, u1, u2;
+            if (a.kind == 0) {
+                u0 = sin(x) * cos(y) * cos(z);
+                u1 = -cos(x) * sin(y) * cos(z);
+                u2 = 0.0;
+            } else {
+                const double A = 2.0, K = 2.0, L = 2.0, M = 2.0;
+                const double lam = sqrt(K * K + L * L + M * M);
+                u0 = -A / (K * K + L * L) * (lam * L * cos(K * x) * sin(L * y) * sin(M * z) + M * K * sin(K * x) * cos(L * y) * cos(M * z));
+                u1 = A / (K * K + L * L) * (lam * K * sin(K * x) * cos(L * y) * sin(M * z) - M * L * cos(K * x) * sin(L * y) * cos(M * z));
+                u2 = A * cos(K * x) * cos(L * y) * sin(M * z);
+            }
+            a.r[0][row * 2 * g.nzp + k] = u0;
+            a.r[1][row * 2 * g.nzp + k] = u1;
+            a.r[2][row * 2 * g.nzp + k] = u2;
+        }
+    }
+}
+
+// Partition independent random-phase solenoidal field: each mode depends only
+// on (seed, kx, ky, kz); Hermitian on the kz = 0 plane by construction.  Bit-identical integer
+// hashing to oracle/ns_oracle.py::_mode_uniform.
+NSB_HD unsigned long long nsb_splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+NSB_HD double nsb_mode_uniform(unsigned long long seed, int kx, int ky, int kz, int c, int j) {
+    const unsigned long long key = (unsigned long long)(kx + 4096) | ((unsigned long long)(ky + 4096) << 16) |
+                                   ((unsigned long long)kz << 32) | ((unsigned long long)c << 48) | ((unsigned long long)j << 52);
+    const unsigned long long h = nsb_splitmix64(nsb_splitmix64(key ^ seed));
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+struct RandArgs {
+    cplx* u[3];
+    Geom g;
+    unsigned long long seed;
+    double kp;
+    int kmax2;
+};
+__global__ void k_ic_random_phase(const RandArgs a) {
+    const Geom g = a.g;
+    const long long nrows = (long long)g.nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        for (int kz = threadIdx.x; kz < g.nzf; kz += blockDim.x) {
+            const long long e = row * g.nzp + kz;
+            const int k2i = kx * kx + ky * ky + kz * kz;
+            cplx v[3] = {mk(0, 0), mk(0, 0), mk(0, 0)};
+            if (k2i != 0 && k2i <= a.kmax2) {
+                const bool neg = (kz == 0) && ((ky < 0) || (ky == 0 && kx < 0));
+                const int cx = neg ? -kx : kx, cy = neg ? -ky : ky;
+                cplx r[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    r[c] = mk(nsb_mode_uniform(a.seed, cx, cy, kz, c, 0) - 0.5, nsb_mode_uniform(a.seed, cx, cy, kz, c, 1) - 0.5);
+                const double k2 = (double)k2i, inv = 1.0 / k2;
+                const cplx kd = mk((double)cx * r[0].x + (double)cy * r[1].x + (double)kz * r[2].x,
+                                   (double)cx * r[0].y + (double)cy * r[1].y + (double)kz * r[2].y);
+                const double kk[3] = {(double)cx, (double)cy, (double)kz};
+                const double shape = sqrt(k2) * exp(-k2 / (a.kp * a.kp));
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    cplx t = mk(r[c].x - kk[c] * inv * kd.x, r[c].y - kk[c] * inv * kd.y);
+                    if (neg) t.y = -t.y;
+                    v[c] = mk(t.x * shape, t.y * shape);
+                }
+            }
+            a.u[0][e] = v[0]; a.u[1][e] = v[1]; a.u[2][e] = v[2];
+        }
+    }
+}

@@ -1,0 +1,143 @@
+/* nsb200.h -- C ABI of libnsb200.so: the B200 (sm_100a) implementation of the pseudospectral RK4
+ * time-step hot path of EndCar808/3D_Navier_Stokes.
+ *
+ * This is the drop-in boundary.  The reference's C host code (main.c, utils.c, SpectralSolve in
+ * solver.c, hdf5_funcs.c) stays as it is; the functions below are what its hot-path functions forward
+ * to (INTEGRATION.md shows the forwarding stubs).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *  - Every function returns 0 on success and non-zero on failure; nsb200_last_error() then holds a
+ *    message.  The forwarding stubs turn a non-zero return into the reference's own error
+ *    behaviour, fprintf(stderr, ...) + exit(1) (e.g. solver.c:2047-2050).
+ *  - A handle is driven by one host thread (the reference is single threaded per rank).  With
+ *    n_ranks > 1 every rank must make the same calls in the same order (as with MPI).
+ *  - Host arrays use the reference layouts:
+ *      Fourier  u_hat[local_Nx][Ny][Nz/2+1][3]  double _Complex, UNNORMALISED forward DFT
+ *               (solver.c:640-645);  element (i,j,k,d) at 3*((Nz/2+1)*(Ny*i + j) + k) + d
+ *      real     u[local_Nx][Ny][Nz+2][3]        double, padded rows (solver.c:667-672)
+ *    `double*` parameters that carry complex data point at interleaved (re, im) pairs, i.e. they
+ *    are the reference's fftw_complex* / double _Complex*.
+ *  - All arithmetic is FP64.  There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef NSB200_H
+#define NSB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsb200_ctx nsb200_ctx;
+
+#define NSB200_DEALIAS_NONE 0
+#define NSB200_DEALIAS_23 1 /* spherical 2/3 rule, integer threshold Nx/3 (solver.c:1732) */
+
+#define NSB200_SYSTEM_NAVIER 0 /* -D__NAVIER: viscous factor in the final update (solver.c:588-603) */
+#define NSB200_SYSTEM_EULER 1  /* -D__EULER  (solver.c:583-587) */
+
+#define NSB200_NMEASURE 20
+
+/* Library / build information: "nsb200 <version> sm_100a". */
+const char* nsb200_version(void);
+/* Message of the last failing call on this thread. */
+const char* nsb200_last_error(void);
+
+/* Replaces AllocateMemory (solver.c:1832-2028) + InitializeFFTWPlans (solver.c:2034-2073) +
+ * InitializeSpaceVariables (solver.c:1764-1826) for the device side.
+ *   N[3]            grid (cubic, power of two, 16..1024; reference accepts any even N, utils.c:86-103)
+ *   device          CUDA device ordinal
+ *   nu, visc_pow    sys_vars->NU and VIS_POW (1.0, or 2.0 for -D__HYPER; data_types.h:68-71)
+ *   system          NSB200_SYSTEM_*
+ *   dealias_mode    NSB200_DEALIAS_*
+ *   rank, n_ranks   slab decomposition over kx exactly like fftw_mpi_local_size_many with
+ *                   FFTW_MPI_DEFAULT_BLOCK (solver.c:1845): local_Nx = Nx / n_ranks planes starting at
+ *                   rank * local_Nx.  n_ranks must divide Nx.
+ *   nccl_unique_id  128-byte ncclUniqueId shared by all ranks (NULL when n_ranks == 1).  The slab
+ *                   exchange inside each 3-D transform is an NCCL all-to-all.                       */
+int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, double visc_pow, int system,
+                  int dealias_mode, int rank, int n_ranks, const void* nccl_unique_id);
+/* Replaces FreeMemory (solver.c:2078-2157). */
+int nsb200_destroy(nsb200_ctx* h);
+/* Writes a fresh 128-byte ncclUniqueId (rank 0 calls this, then broadcasts it with MPI_Bcast or
+ * torch.distributed). */
+int nsb200_get_nccl_unique_id(void* out128);
+
+/* sys_vars->local_Nx / local_Nx_start as fftw_mpi_local_size_many reports them (solver.c:1845). */
+int nsb200_local_slab(nsb200_ctx* h, long* local_nx, long* local_nx_start);
+/* Number of double _Complex elements of a local Fourier vector field (= alloc_local_batch). */
+long nsb200_local_fourier_elems(nsb200_ctx* h);
+
+/* run_data->u_hat  <->  device state (the state lives on the GPU between steps). */
+int nsb200_upload_uhat(nsb200_ctx* h, const double* u_hat_host);
+int nsb200_download_uhat(nsb200_ctx* h, double* u_hat_host);
+
+/* Replaces RK4Step(dt, N, local_Nx, RK_data) (solver.c:505-608): one RK4 step of the resident
+ * state, four NonlinearRHSBatch evaluations, viscous (or Euler) final update. */
+int nsb200_rk4_step(nsb200_ctx* h, double dt);
+/* n_steps calls of nsb200_rk4_step without returning to the host in between. */
+int nsb200_rk4_steps(nsb200_ctx* h, double dt, int n_steps);
+
+/* Replaces NonlinearRHSBatch(u_hat, dw_hat_dt, curl, u, vort) (solver.c:620-731) for host arrays:
+ * dw_hat_dt = dealias(P[ (u x w)^ ]) / (NxNyNz)^2.  u_hat_in is not modified (FFTW_PRESERVE_INPUT). */
+int nsb200_nonlinear_rhs(nsb200_ctx* h, const double* u_hat_in, double* dw_hat_dt_out);
+
+/* Replaces ApplyDealiasing(array, array_dim, N) (solver.c:1709-1756, with fix F2: kept modes are
+ * left untouched) on a host array [local_Nx][Ny][Nz/2+1][array_dim] complex, in place. */
+int nsb200_apply_dealiasing(nsb200_ctx* h, double* array_host, int array_dim);
+
+/* Replaces the sums of ComputeSystemMeasurables(iter) (solver.c:1186-1263) on the resident state.
+ * out[20] (global sums over all ranks; edge = kz in {0, Nz/2}, interior = the rest):
+ *   [0..2]  sum_edge |u_d|^2          [3..5]   sum_interior |u_d|^2
+ *   [6..8]  sum_edge |w_d|^2          [9..11]  sum_interior |w_d|^2        w = i k x u
+ *   [12..14] sum_edge |(i k x w)_d|^2 [15..17] sum_interior |(i k x w)_d|^2
+ *   [18] sum wgt Re(u . w)  (plain product)      [19] sum wgt nu |k|^(2 visc_pow) |u|^2
+ * with wgt = 1 on the edge planes and 2 inside.  nsb200_assemble_measurables turns them into the five
+ * series values either literally as solver.c:1224-1235 computes them (operator-precedence defect
+ * F4: the factor 2 multiplies the x component only) or correctly parenthesised (solver.c:855-857). */
+int nsb200_measure(nsb200_ctx* h, double out[NSB200_NMEASURE]);
+/* values[5] = { tot_energy, tot_enstr, tot_palin, tot_heli, enrg_diss } incl. the normalisation of
+ * solver.c:1270-1274.  literal != 0 reproduces the reference's precedence. */
+int nsb200_assemble_measurables(const double partial[NSB200_NMEASURE], const long N[3], int literal, double values[5]);
+
+/* Shell spectra as ComputeSystemMeasurables bins them (solver.c:1240-1259): bin = round(|k|), n_spect =
+ * (int)sqrt(3 (N/2)^2) + 1 (solver.c:1384).  enrg / enst: n_spect doubles each (either may be NULL). */
+int nsb200_spectra(nsb200_ctx* h, double* enrg_spect, double* enst_spect, int n_spect);
+
+/* Replaces the non-transposed batch plans fftw_3d_dft_batch_r2c / _c2r (solver.c:2056-2057) as used by
+ * InitialConditions (solver.c:1573,1599) and the real-space dumps (hdf5_funcs.c:588,665): three
+ * interleaved components, unnormalised, host arrays in the reference layouts.  Single rank only. */
+int nsb200_fft_r2c(nsb200_ctx* h, const double* real_in, double* cplx_out);
+int nsb200_fft_c2r(nsb200_ctx* h, const double* cplx_in, double* real_out);
+
+/* Replaces InitialConditions (solver.c:1537-1648, fixes F3/F5) on the device: "TAYLOR_GREEN",
+ * "SHAPIRO" (real-space fill, batch r2c, dealias) or "RANDOM_PHASE" (the partition-independent
+ * synthetic field of SURVEY 8d: seed, peak wavenumber kp, rescaled to `energy`). */
+int nsb200_initial_condition(nsb200_ctx* h, const char* name, unsigned long long seed, double kp, double energy);
+
+/* Pin / unpin a host buffer (e.g. run_data->u_hat) so upload/download run at full PCIe rate. */
+int nsb200_host_register(void* ptr, unsigned long long bytes);
+int nsb200_host_unregister(void* ptr);
+
+/* ---- measurement hooks (bench.py): run an operation `iters` times on the handle's own stream and
+ * return the elapsed device time in milliseconds measured with CUDA events on that stream.
+ *   NSB200_OP_RK4_STEP        one full time step (dt given)
+ *   NSB200_OP_FFT_C2R_R2C     one batched (3 fields) c2r followed by r2c on device workspace
+ *   NSB200_OP_PASS_Y / _X / _Z  a single inverse 1-D pass over 3 fields (roofline of one pass)
+ *   NSB200_OP_L2_FLUSH        overwrite a buffer larger than L2                                   */
+#define NSB200_OP_RK4_STEP 0
+#define NSB200_OP_FFT_C2R_R2C 1
+#define NSB200_OP_PASS_Y 2
+#define NSB200_OP_PASS_X 3
+#define NSB200_OP_PASS_Z 4
+#define NSB200_OP_L2_FLUSH 5
+#define NSB200_OP_Z_FUSED 6
+#define NSB200_OP_RK_POINTWISE 7
+int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_ms);
+/* Kernels launched by this handle since creation (bench.py's gpu_launches). */
+long nsb200_launch_count(nsb200_ctx* h);
+/* Bytes of device memory held by the handle. */
+long nsb200_device_bytes(nsb200_ctx* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSB200_H */
