@@ -34,10 +34,14 @@ SYMBOLS = [
     ("nsb200_host_register", ctypes.c_int, [ctypes.c_void_p, ctypes.c_ulonglong]),
     ("nsb200_host_unregister", ctypes.c_int, [ctypes.c_void_p]),
     ("nsb200_time_op", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, _DP]),
+    ("nsb200_profile", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    ("nsb200_profile_read", ctypes.c_int, [ctypes.c_void_p, _DP, _LP]),
     ("nsb200_launch_count", ctypes.c_long, [ctypes.c_void_p]),
     ("nsb200_device_bytes", ctypes.c_long, [ctypes.c_void_p]),
 ]
 
+PC_NAMES = ["curl", "y_inv", "x_inv", "z_fused", "x_fwd", "y_fwd", "rk", "z_c2r", "z_r2c"]
+PC_COUNT = 16
 OP_RK4_STEP, OP_FFT_C2R_R2C, OP_PASS_Y, OP_PASS_X, OP_PASS_Z, OP_L2_FLUSH, OP_Z_FUSED, OP_RK_POINTWISE = range(8)
 
 

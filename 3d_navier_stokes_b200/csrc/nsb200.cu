@@ -135,12 +135,35 @@ struct nsb200_ctx {
     int zgrid[3] = {0, 0, 0};
     long launches = 0;
     size_t bytes = 0;
+    bool prof_on = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
     Geom geom() const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.x_start = x_start; return g; }
     long long nrows() const { return (long long)nx_loc * N; }
     int row_grid() const { long long r = nrows(); long long cap = (long long)sm_count * 32; return (int)(r < cap ? r : cap); }
 };
 
 static int set_device(nsb200_ctx* h) { CK(cudaSetDevice(h->device)); return 0; }
+
+// ------------------------------------------------------------------------------ per-kernel-class timing
+// When enabled, every launch is bracketed by CUDA events on the launching stream; bench.py reads the
+// per-class sums after the timed region (NSB200_PC_* in nsb200.h).
+static cudaEvent_t prof_event(nsb200_ctx* h) {
+    if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    nsb200_ctx* h; cudaEvent_t a = nullptr, b = nullptr; int cls;
+    ProfScope(nsb200_ctx* h_, int cls_) : h(h_), cls(cls_) {
+        if (h->prof_on) { a = prof_event(h); b = prof_event(h); cudaEventRecord(a, h->stream); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEventRecord(b, h->stream); h->prof.push_back({cls, a, b}); }
+    }
+};
 
 // ------------------------------------------------------------------------------ transform plumbing
 // One strided c2c pass.  axis 'y': Fourier slab [kx_loc][ky][kz], outer = kx_loc.  axis 'x': after the slab
@@ -177,7 +200,10 @@ static int run_pass(nsb200_ctx* h, char axis, int dir, int nfields, cplx* const*
         a.in_so = a.out_so = nzp;
         a.in_s2 = a.out_s2 = (long long)h->ny_loc * nzp;
     }
-    CKI(h->ops->strided(dir, &a, n_outer, field_cnt, h->stream));
+    {
+        ProfScope ps(h, axis == 'y' ? (dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD));
+        CKI(h->ops->strided(dir, &a, n_outer, field_cnt, h->stream));
+    }
     h->launches++;
     return 0;
 }
@@ -193,7 +219,10 @@ static int run_z(nsb200_ctx* h, int which, int nfields, cplx* const* f) {
     a.kz_out = h->nzf;
     long long want = (a.npairs + h->ops->z_pairs_per_cta - 1) / h->ops->z_pairs_per_cta;
     int grid = (int)(want < h->zgrid[which] ? want : h->zgrid[which]);
-    CKI(h->ops->z(which, &a, nfields, grid, h->stream));
+    {
+        ProfScope ps(h, which == NSB_Z_FUSED ? NSB200_PC_Z_FUSED : which == NSB_Z_C2R ? NSB200_PC_Z_C2R : NSB200_PC_Z_R2C);
+        CKI(h->ops->z(which, &a, nfields, grid, h->stream));
+    }
     h->launches++;
     return 0;
 }
@@ -218,7 +247,10 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in) {
     CurlArgs ca;
     for (int d = 0; d < 3; ++d) { ca.u[d] = in[d]; ca.w[d] = h->R[3 + d]; }
     ca.g = h->geom();
-    k_curl<<<rg, 128, 0, h->stream>>>(ca);
+    {
+        ProfScope ps(h, NSB200_PC_CURL);
+        k_curl<<<rg, 128, 0, h->stream>>>(ca);
+    }
     CK(cudaGetLastError());
     h->launches++;
     cplx* src[6] = {in[0], in[1], in[2], h->R[3], h->R[4], h->R[5]};
@@ -269,7 +301,10 @@ static int rk_stage(nsb200_ctx* h, int stage, double dt) {
     a.dt = dt; a.nu = h->nu; a.visc_pow = h->visc_pow;
     const double n3 = (double)h->N * (double)h->N * (double)h->N;
     a.norm = 1.0 / (n3 * n3);   // 1/pow(Nx*Ny*Nz, 2.0), solver.c:631 (exact for powers of two)
-    k_rk_stage<<<h->row_grid(), 128, 0, h->stream>>>(a);
+    {
+        ProfScope ps(h, NSB200_PC_RK);
+        k_rk_stage<<<h->row_grid(), 128, 0, h->stream>>>(a);
+    }
     CK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -320,6 +355,8 @@ int nsb200_destroy(nsb200_ctx* h) {
     cudaFree(h->slab); cudaFree(h->tw); cudaFree(h->meas_partial); cudaFree(h->meas_dev); cudaFree(h->spect_dev);
     cudaFree(h->flush_buf);
     if (h->meas_host) cudaFreeHost(h->meas_host);
+    for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
     for (auto e : h->ev_field) cudaEventDestroy(e);
     for (auto e : h->ev_comm) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -667,6 +704,28 @@ int nsb200_spectra(nsb200_ctx* h, double* enrg_spect, double* enst_spect, int n_
     CK(cudaStreamSynchronize(h->stream));
     if (enrg_spect) memcpy(enrg_spect, h->meas_host, sizeof(double) * n_spect);
     if (enst_spect) memcpy(enst_spect, h->meas_host + 2048, sizeof(double) * n_spect);
+    return 0;
+}
+
+int nsb200_profile(nsb200_ctx* h, int enable) {
+    if (!h) return fail("nsb200_profile: null handle");
+    h->prof_on = enable != 0;
+    return 0;
+}
+int nsb200_profile_read(nsb200_ctx* h, double ms[NSB200_PC_COUNT], long counts[NSB200_PC_COUNT]) {
+    if (!h || !ms || !counts) return fail("nsb200_profile_read: null argument");
+    CKR(set_device(h));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < NSB200_PC_COUNT; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    for (auto& r : h->prof) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cls] += (double)t;
+        counts[r.cls]++;
+        h->ev_pool.push_back(r.a);
+        h->ev_pool.push_back(r.b);
+    }
+    h->prof.clear();
     return 0;
 }
 

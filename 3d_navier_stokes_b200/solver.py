@@ -160,6 +160,16 @@ class Solver:
         self.lib.check(self.lib.nsb200_time_op(self.h, int(op), int(iters), float(dt), ctypes.byref(ms)), "nsb200_time_op")
         return ms.value
 
+    def profile(self, enable):
+        self.lib.check(self.lib.nsb200_profile(self.h, 1 if enable else 0), "nsb200_profile")
+
+    def profile_read(self):
+        """{class name: (summed ms, launches)} since the last read."""
+        ms = (ctypes.c_double * capi.PC_COUNT)()
+        cnt = (ctypes.c_long * capi.PC_COUNT)()
+        self.lib.check(self.lib.nsb200_profile_read(self.h, ms, cnt), "nsb200_profile_read")
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(capi.PC_NAMES) if cnt[i]}
+
     def launch_count(self):
         return int(self.lib.nsb200_launch_count(self.h))
 

@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Headline benchmark: time steps per second of the pseudospectral RK4 hot path.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Our arm: random-phase decaying turbulence at 512^3 FP64 (BASELINE.json configs[2], the configuration
+the metric is quoted on that fits one GPU), state resident in HBM, K RK4 steps timed with CUDA events
+on the library's own stream (nsb200_time_op), max over ranks.  One JSON line on stdout (rank 0).
+
+Reference arm: the reference's own C (oracle/_ref: solver.c compiled unchanged apart from the
+documented fixes F1-F3 on a single-rank FFTW-MPI shim; FFTW/MPI/HDF5 are not in this image) timed on
+the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "timesteps_per_sec"
+UNIT = "steps/s"
+NU = 1e-3
+DT = 1e-3
+SEED = 123456789
+KP = 4.0
+
+
+def scalar_bytes(n):
+    return 8.0 * n * n * (n + 2)
+
+
+def workload_config(n, n_gpus):
+    return {
+        "workload": "random-phase decaying turbulence %d^3 FP64 RK4 (BASELINE.json configs[2]; E(k)~k^4 exp(-2(k/4)^2), E=pi^3)" % n,
+        "N": n, "nu": NU, "dt": DT, "ic": "RANDOM_PHASE seed=%d kp=%g" % (SEED, KP),
+        "dealias": "2/3 spherical, integer threshold N/3", "viscosity": "nu k^2 (CN factor in the final update)",
+        "parallelism": "kx slabs x %d, NCCL all-to-all inside each 3-D transform" % n_gpus if n_gpus > 1 else "single GPU",
+        "l2": "no flush: every pass streams fields of %.2f GB each (>> 126 MB L2)" % (scalar_bytes(n) / 1e9),
+    }
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, torch copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def reference_arm(n, steps, warmup, budget_s, n_gpus):
+    """Times the reference's own RK4Step / NonlinearRHSBatch (oracle/_ref) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_lib as R
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(n, n_gpus)}
+    if not R.available():
+        base.update({"unavailable": "oracle/_ref/libns_ref.so missing (built by `make -C oracle` where /root/reference exists)"})
+        return base
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(devnull, 1)          # the reference prints its wavenumber table on set-up
+    try:
+        t_all = time.time()
+        # pilot at 128^3 to choose the largest sample that fits the budget
+        r = R.RefSolver(128, nu=NU, dt=DT, ic="TAYLOR_GREEN")
+        r.nonlinear_timing()
+        t0 = time.time(); r.nonlinear_timing(); t_nl128 = time.time() - t0
+        r.close()
+
+        def predict_nl(m):   # N^3 log N scaling of one NonlinearRHSBatch
+            return t_nl128 * (m / 128.0) ** 3 * (math.log2(m) / 7.0)
+
+        total = max(1, steps + warmup)
+        per = budget_s / total
+        grid, mode = None, None
+        for m in (n, n // 2, n // 4):
+            if m < 64:
+                break
+            need_gb = 12 * 3 * scalar_bytes(m) / 1e9 * 1.25
+            if mem_available_gb() < need_gb:
+                continue
+            if 4.6 * predict_nl(m) <= per:
+                grid, mode = m, "step"; break
+            if predict_nl(m) <= per:
+                grid, mode = m, "nl"; break
+        if grid is None:
+            grid, mode = 128, "nl"
+        r = R.RefSolver(grid, nu=NU, dt=DT, ic="TAYLOR_GREEN")
+        fn = (lambda: r.rk4_step(DT)) if mode == "step" else r.nonlinear_timing
+        for _ in range(warmup):
+            fn()
+        times = []
+        for _ in range(steps):
+            t0 = time.time(); fn(); times.append(time.time() - t0)
+            if time.time() - t_all > 2.5 * budget_s and len(times) >= 1:
+                break
+        r.close()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(devnull)
+    t = sum(times) / len(times)
+    # scale the sample to one full time step of the n^3 workload
+    scale = 1.0
+    what = "full RK4Step"
+    if mode == "nl":
+        scale *= 4.0 * 1.12   # 4 NonlinearRHSBatch per step + stage/update sweeps (measured ~12 % at 256^3)
+        what = "one NonlinearRHSBatch (1 of the 4 per step; x4.48 incl. RK sweeps)"
+    if grid != n:
+        f = (n / grid) ** 3 * (math.log2(n) / math.log2(grid))
+        scale *= f
+        what += " at %d^3 scaled x%.2f (N^3 log N) to %d^3" % (grid, f, n)
+    sec_per_step = t * scale
+    val = 1.0 / sec_per_step
+    sample = ("%s, %d timed sample(s) of %.2f s, Taylor-Green data (cost is data independent); reference solver.c loops "
+              "(serial per rank, 1 rank) + OpenMP shim FFT on %d threads, NOT FFTW/MPI" % (what, len(times), t, cores))
+    base.update({"value": val, "ms_per_step": 1e3 * sec_per_step, "samples_timed": len(times),
+                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return base
+
+
+# ------------------------------------------------------------------------------------------ our arm
+# algorithmic bytes per launch in units of S = bytes of one scalar field (DESIGN.md "kernels")
+ALGO_S = {"curl": 6.0, "y_inv": 12.0, "x_inv": 12.0, "z_fused": 9.0, "x_fwd": 6.0, "y_fwd": 6.0, "rk": 13.5}
+
+
+def ours(args):
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libnsb200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    nsb = importlib.import_module("3d_navier_stokes_b200")
+    capi = importlib.import_module("3d_navier_stokes_b200.capi")
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(nsb.Solver.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.n
+    S = scalar_bytes(n)
+    s = nsb.Solver(n, nu=NU, device=local, rank=rank, n_ranks=world, nccl_unique_id=uid)
+    s.initial_conditions("RANDOM_PHASE", seed=SEED, kp=KP, energy=math.pi ** 3)
+    e0 = s.compute_system_measurables()
+    # pinned host copy of the local slab for the end-to-end leg
+    host = torch.empty(s.shape_f, dtype=torch.complex128).pin_memory()
+    s.download_ptr(host.data_ptr())
+    slab_bytes = host.numel() * 16
+
+    # ---- device-resident timing
+    s.time_op(capi.OP_RK4_STEP, max(args.warmup, 3), DT)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    s.profile(True)
+    l0 = s.launch_count()
+    barrier()
+    ms = s.time_op(capi.OP_RK4_STEP, args.steps, DT)
+    barrier()
+    launches = s.launch_count() - l0
+    prof = s.profile_read()
+    s.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+    e1 = s.compute_system_measurables()
+
+    # ---- end to end through the C ABI with host buffers: one save interval of K steps
+    #      (upload u_hat from pinned host, K x [RK4Step + ComputeSystemMeasurables -> host], download u_hat)
+    barrier()
+    t0 = time.perf_counter()
+    s.upload_ptr(host.data_ptr())
+    series = []
+    for _ in range(args.steps):
+        s.rk4_step(DT)
+        series.append(s.measure_partials())
+    s.download_ptr(host.data_ptr())
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_val = args.steps / t_e2e
+    # worst case: host owns the state every step (a naive per-call binding of RK4Step)
+    k2 = min(args.steps, 3)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k2):
+        s.upload_ptr(host.data_ptr())
+        s.rk4_step(DT)
+        s.download_ptr(host.data_ptr())
+    barrier()
+    t_sync = max_over_ranks(time.perf_counter() - t0) / k2
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        tot_prof = sum(v[0] for v in prof.values()) or 1.0
+        dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else "z_fused"
+        dom_ms, dom_cnt = prof.get(dom, (0.0, 0))
+        per_launch_ms = dom_ms / max(dom_cnt, 1)
+        algo_bytes = ALGO_S[dom] * S / world
+        achieved = algo_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr.get("%s_%d" % (dom, n))
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": per_launch_ms,
+                         "share_of_step": dom_ms / tot_prof,
+                         "step_frac_204S": 204.0 * S / world / (ms_per_step * 1e-3) / 1e9 / peak},
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": slab_bytes * world / args.steps,
+                    "d2h_bytes_per_step": slab_bytes * world / args.steps + 160.0 * world,
+                    "what": "one save interval through the C ABI with pinned host buffers: upload u_hat, %d x (RK4Step + "
+                            "ComputeSystemMeasurables to host), download u_hat; host wall clock around synchronous calls" % args.steps,
+                    "host_state_every_step": {"value": 1.0 / t_sync, "unit": UNIT,
+                                              "h2d_bytes_per_step": slab_bytes * world, "d2h_bytes_per_step": slab_bytes * world}},
+            "gpu_launches": launches * world,
+            "clocks": clocks,
+            "energy_start_end": [float(e0[0]), float(e1[0])],
+            "device_bytes_per_gpu": s.device_bytes(),
+        }
+    s.close()
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            try:
+                p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                    "--budget", "25", "--n", str(n)], capture_output=True, text=True, timeout=600)
+                line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+                out["cpu_baseline"] = json.loads(line).get("cpu_baseline", {"unavailable": json.loads(line).get("unavailable")})
+            except Exception as ex:   # the bench line must still be printed
+                out["cpu_baseline"] = {"unavailable": "cpu leg failed: %r" % (ex,)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="grid size (default: the BASELINE workload, 512)")
+    ap.add_argument("--budget", type=float, default=150.0, help="reference arm: seconds of CPU work for all steps")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        print(json.dumps(reference_arm(args.n, args.steps, args.warmup, args.budget, args.gpus)))
+        return
+    ours(args)
+
+
+if __name__ == "__main__":
+    main()

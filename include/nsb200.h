@@ -132,6 +132,21 @@ int nsb200_host_unregister(void* ptr);
 #define NSB200_OP_Z_FUSED 6
 #define NSB200_OP_RK_POINTWISE 7
 int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_ms);
+/* Per-kernel-class timing: while enabled every kernel launch of the handle is bracketed by CUDA events
+ * on the launching stream; nsb200_profile_read synchronises, returns the summed device time (ms) and
+ * launch count per class since the last read, and clears the records. */
+#define NSB200_PC_CURL 0   /* spectral curl                      (solver.c:637-650) */
+#define NSB200_PC_Y_INV 1  /* inverse c2c pass along y, 6 fields (inside solver.c:656,658) */
+#define NSB200_PC_X_INV 2  /* inverse c2c pass along x, 6 fields */
+#define NSB200_PC_Z_FUSED 3 /* z c2r -> u x w -> z r2c          (solver.c:656-683) */
+#define NSB200_PC_X_FWD 4  /* forward c2c pass along x, 3 fields (inside solver.c:683) */
+#define NSB200_PC_Y_FWD 5  /* forward c2c pass along y, 3 fields */
+#define NSB200_PC_RK 6     /* normalise/project/dealias + RK update (solver.c:689-727, 523-607) */
+#define NSB200_PC_Z_C2R 7
+#define NSB200_PC_Z_R2C 8
+#define NSB200_PC_COUNT 16
+int nsb200_profile(nsb200_ctx* h, int enable);
+int nsb200_profile_read(nsb200_ctx* h, double ms[NSB200_PC_COUNT], long counts[NSB200_PC_COUNT]);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 long nsb200_launch_count(nsb200_ctx* h);
 /* Bytes of device memory held by the handle. */
