@@ -154,6 +154,16 @@ template <> struct ZPlan<256> { typedef FftPlan<256, 4, 8, 8> type; };
 template <> struct ZPlan<512> { typedef FftPlan<512, 8, 8, 8> type; };
 template <> struct ZPlan<1024> { typedef FftPlan<1024, 8, 8, 16> type; };
 
+// fused z kernel plans: balanced (R1 == R_last), see k_z_fused
+template <int N> struct ZFPlan;
+template <> struct ZFPlan<16> { typedef FftPlan<16, 4, 4, 1> type; };
+template <> struct ZFPlan<32> { typedef FftPlan<32, 4, 2, 4> type; };
+template <> struct ZFPlan<64> { typedef FftPlan<64, 8, 8, 1> type; };
+template <> struct ZFPlan<128> { typedef FftPlan<128, 4, 8, 4> type; };
+template <> struct ZFPlan<256> { typedef FftPlan<256, 8, 4, 8> type; };
+template <> struct ZFPlan<512> { typedef FftPlan<512, 8, 8, 8> type; };
+template <> struct ZFPlan<1024> { typedef FftPlan<1024, 16, 4, 16> type; };
+
 template <class P> NSB_HD int padi(int i) { return i + i / P::M1; }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,10 +11,11 @@
 namespace {
 typedef BigPlan<NSB_N>::type BP;
 typedef ZPlan<NSB_N>::type ZP;
+typedef ZFPlan<NSB_N>::type ZF;
 constexpr int ST = StridedCfg<NSB_N>::T, STP = StridedCfg<NSB_N>::TP;
 constexpr size_t kStridedSmem = (size_t)BP::NPAD * ST * sizeof(cplx);
 constexpr size_t kZSmem = (size_t)ZP::NPAD * ZCfg<ZP>::G * sizeof(cplx);
-constexpr size_t kZFusedSmem = 6 * kZSmem;
+constexpr size_t kZFusedSmem = (size_t)6 * ZF::NPAD * ZFusedCfg<ZF>::G * sizeof(cplx);
 
 int setup() {
     cudaError_t e;
@@ -26,7 +27,7 @@ int setup() {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_z_r2c<ZP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZSmem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_z_fused<ZP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZFusedSmem);
+    e = cudaFuncSetAttribute(k_z_fused<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZFusedSmem);
     return (int)e;
 }
 
@@ -43,7 +44,7 @@ int zlaunch(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s) 
     constexpr int TH = ZCfg<ZP>::THREADS;
     if (which == NSB_Z_C2R) k_z_c2r<ZP><<<dim3(grid_x, nfields), TH, kZSmem, s>>>(*a);
     else if (which == NSB_Z_R2C) k_z_r2c<ZP><<<dim3(grid_x, nfields), TH, kZSmem, s>>>(*a);
-    else k_z_fused<ZP><<<dim3(grid_x), TH, kZFusedSmem, s>>>(*a);
+    else k_z_fused<ZF><<<dim3(grid_x), ZFusedCfg<ZF>::THREADS, kZFusedSmem, s>>>(*a);
     return (int)cudaGetLastError();
 }
 
@@ -52,9 +53,9 @@ int zocc(int which) {
     constexpr int TH = ZCfg<ZP>::THREADS;
     if (which == NSB_Z_C2R) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_c2r<ZP>, TH, kZSmem);
     else if (which == NSB_Z_R2C) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_r2c<ZP>, TH, kZSmem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused<ZP>, TH, kZFusedSmem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused<ZF>, ZFusedCfg<ZF>::THREADS, kZFusedSmem);
     return n;
 }
 }  // namespace
 
-extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, ZCfg<ZP>::G, setup, strided, zlaunch, zocc};
+extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G}, setup, strided, zlaunch, zocc};

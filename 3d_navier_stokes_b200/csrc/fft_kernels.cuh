@@ -198,23 +198,51 @@ NSB_HD cplx cross_comp(cplx a1, cplx b2, cplx a2, cplx b1) {
     return mk(NSB_SUB(NSB_MUL(a1.x, b2.x), NSB_MUL(a2.x, b1.x)), NSB_SUB(NSB_MUL(a1.y, b2.y), NSB_MUL(a2.y, b1.y)));
 }
 
+// Fused z kernel.  One pencil PAIR (two adjacent rows, packed as real/imag of one complex transform) is
+// owned by three teams of TP threads:
+//   inverse  team t transforms fields 2t, 2t+1 of (ux, uy, uz, wx, wy, wz)
+//   product  team t forms component t of u x w at its R1 points and runs forward pass 1 on it in registers
+//   forward  team t finishes component t and stores the two half spectra
+// The plan is balanced (R1 == R_last), so the thread that produced real-space points {q + j*N/R1} in the
+// last inverse pass is the one that consumes them in the first forward pass: the last inverse pass
+// writes its outputs back IN PLACE (its own shared-memory row), no natural-order shuffle is needed and
+// the six real-space fields of the pair never leave the SM.
+template <class P> struct ZFusedCfg {
+    static_assert(P::R1 == P::RL, "fused z kernel needs a balanced plan (first radix == last radix)");
+    static constexpr int TP = P::NB1;
+    static constexpr int TEAM = 3 * TP;
+    static constexpr int G = (TEAM >= 96) ? 1 : (96 / TEAM);
+    static constexpr int THREADS = TEAM * G;
+    // resident CTAs per SM the register allocation must allow: as many as shared memory admits, capped so
+    // that a thread keeps >= 80 registers
+    static constexpr int SMEM = 6 * P::NPAD * G * 16;
+    static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
+    static constexpr int BY_REGS = 65536 / (THREADS * 80);
+    static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
+};
+
 template <class P>
-__global__ void __launch_bounds__(ZCfg<P>::THREADS) k_z_fused(const ZArgs a) {
-    constexpr int N = P::N, TP = ZCfg<P>::TP, G = ZCfg<P>::G, NP = P::NPAD;
+__global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z_fused(const ZArgs a) {
+    constexpr int N = P::N, TP = ZFusedCfg<P>::TP, G = ZFusedCfg<P>::G, NP = P::NPAD, TEAM = ZFusedCfg<P>::TEAM;
     extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
     cplx* smem = reinterpret_cast<cplx*>(nsb_smem_raw);
-    const int s = threadIdx.x / TP, q = threadIdx.x % TP;
+    const int s = threadIdx.x / TEAM;
+    const int t = (threadIdx.x % TEAM) / TP;      // team = output component
+    const int q = threadIdx.x % TP;
     cplx* sm = smem + (size_t)s * 6 * NP;
     const cplx* __restrict__ tw = a.tw;
     const int kzin = a.kz_in, kzout = a.kz_out;
+    // this thread's row in the in-place layout (same indexing as fft_pass_last with b = q)
+    const int rowbase = (q % P::R1) * (P::M1 + 1) + (q / P::R1) * P::RL;
     for (long long pr0 = (long long)blockIdx.x * G; pr0 < a.npairs; pr0 += (long long)gridDim.x * G) {
         const long long pr = pr0 + s;
         const bool ok = pr < a.npairs;
         const long long roff = 2 * pr * a.rs;
-        // ---- inverse z transforms of u (fields 0..2) and w (fields 3..5)
+        // ---- inverse transforms: team t owns fields 2t and 2t+1
         if (ok) {
 #pragma unroll
-            for (int f = 0; f < 6; ++f) {
+            for (int ff = 0; ff < 2; ++ff) {
+                const int f = 2 * t + ff;
                 const cplx* ra = a.f[f] + roff;
                 const cplx* rb = ra + a.rs;
                 fft_pass1<P, INV, 1>(q, sm + f * NP, tw, [&](int n) {
@@ -226,84 +254,66 @@ __global__ void __launch_bounds__(ZCfg<P>::THREADS) k_z_fused(const ZArgs a) {
         }
         __syncthreads();
         if constexpr (P::PASSES == 3) {
-            if (ok && q < P::NB2) {
+            if (ok) {
 #pragma unroll
-                for (int f = 0; f < 6; ++f) fft_pass2<P, INV, 1>(q, sm + f * NP, tw);
+                for (int ff = 0; ff < 2; ++ff)
+                    for (int b = q; b < P::NB2; b += TP) fft_pass2<P, INV, 1>(b, sm + (2 * t + ff) * NP, tw);
             }
             __syncthreads();
         }
+        if (ok) {
 #pragma unroll
-        for (int f = 0; f < 6; f += 2) {
-            cplx v0[P::RL], v1[P::RL];
-            if (ok && q < P::NBL) {
-                fft_pass_last<P, INV, 1>(q, sm + f * NP, v0);
-                fft_pass_last<P, INV, 1>(q, sm + (f + 1) * NP, v1);
-            }
-            __syncthreads();
-            if (ok && q < P::NBL) {
+            for (int ff = 0; ff < 2; ++ff) {
+                cplx v[P::RL];
+                cplx* buf = sm + (2 * t + ff) * NP;
+                fft_pass_last<P, INV, 1>(q, buf, v);      // v[j] = field(n = q + j * N/RL)
 #pragma unroll
-                for (int k2 = 0; k2 < P::RL; ++k2) {
-                    sm[f * NP + q + k2 * P::NBL] = v0[k2];
-                    sm[(f + 1) * NP + q + k2 * P::NBL] = v1[k2];
-                }
+                for (int j = 0; j < P::RL; ++j) buf[rowbase + j] = v[j];
             }
         }
         __syncthreads();
-        // ---- real-space cross product feeding pass 1 of the forward transforms
-        {
-            cplx cx[P::R1], cy[P::R1], cz[P::R1];
-            if (ok) {
+        // ---- u x w at this thread's points, straight into forward pass 1 (registers)
+        cplx c[P::R1];
+        if (ok) {
+            // component t = u_{t+1} w_{t+2} - u_{t+2} w_{t+1}   (indices mod 3; w fields are 3..5)
+            const int i1 = (t + 1) % 3, i2 = (t + 2) % 3;
+            const cplx* u1 = sm + i1 * NP + rowbase;
+            const cplx* u2 = sm + i2 * NP + rowbase;
+            const cplx* w1 = sm + (3 + i1) * NP + rowbase;
+            const cplx* w2 = sm + (3 + i2) * NP + rowbase;
 #pragma unroll
-                for (int j = 0; j < P::R1; ++j) {
-                    const int n = q + j * P::M1;
-                    const cplx ux = sm[n], uy = sm[NP + n], uz = sm[2 * NP + n];
-                    const cplx wx = sm[3 * NP + n], wy = sm[4 * NP + n], wz = sm[5 * NP + n];
-                    cx[j] = cross_comp(uy, wz, uz, wy);
-                    cy[j] = cross_comp(uz, wx, ux, wz);
-                    cz[j] = cross_comp(ux, wy, uy, wx);
-                }
-                fft_pass1_regs<P, FWD>(q, cx, tw);
-                fft_pass1_regs<P, FWD>(q, cy, tw);
-                fft_pass1_regs<P, FWD>(q, cz, tw);
-            }
-            __syncthreads();
-            if (ok) {
-                fft_pass1_scatter<P, 1>(q, sm, cx);
-                fft_pass1_scatter<P, 1>(q, sm + NP, cy);
-                fft_pass1_scatter<P, 1>(q, sm + 2 * NP, cz);
-            }
+            for (int j = 0; j < P::R1; ++j) c[j] = cross_comp(u1[j], w2[j], u2[j], w1[j]);
+            fft_pass1_regs<P, FWD>(q, c, tw);
         }
+        __syncthreads();
+        if (ok) fft_pass1_scatter<P, 1>(q, sm + t * NP, c);
         __syncthreads();
         if constexpr (P::PASSES == 3) {
-            if (ok && q < P::NB2) {
-#pragma unroll
-                for (int f = 0; f < 3; ++f) fft_pass2<P, FWD, 1>(q, sm + f * NP, tw);
-            }
+            if (ok)
+                for (int b = q; b < P::NB2; b += TP) fft_pass2<P, FWD, 1>(b, sm + t * NP, tw);
             __syncthreads();
         }
-        {
-            // last pass of the three forward transforms; outputs go, in natural order, to buffers 3..5
-            // (dead since the cross product) so no barrier is needed between gather and scatter
-            if (ok && q < P::NBL) {
+        cplx v[P::RL];
+        if (ok) {
+            cplx* buf = sm + t * NP;
+            fft_pass_last<P, FWD, 1>(q, buf, v);          // v[j] = Z(k = q + j * N/RL)
 #pragma unroll
-                for (int f = 0; f < 3; ++f) {
-                    cplx v[P::RL];
-                    fft_pass_last<P, FWD, 1>(q, sm + f * NP, v);
-#pragma unroll
-                    for (int k2 = 0; k2 < P::RL; ++k2) sm[(3 + f) * NP + q + k2 * P::NBL] = v[k2];
-                }
-            }
+            for (int j = 0; j < P::RL; ++j) buf[rowbase + j] = v[j];
         }
         __syncthreads();
         if (ok) {
+            cplx* ra = a.f[t] + roff;
+            cplx* rb = ra + a.rs;
+            const cplx* buf = sm + t * NP;
 #pragma unroll
-            for (int f = 0; f < 3; ++f) {
-                cplx* ra = a.f[f] + roff;
-                cplx* rb = ra + a.rs;
-                const cplx* z = sm + (3 + f) * NP;
-                for (int k = q; k <= N / 2 && k < kzout; k += TP) {
+            for (int j = 0; j <= P::RL / 2; ++j) {
+                const int k = q + j * P::NBL;
+                if (k <= N / 2 && k < kzout) {
+                    const int m = (N - k) & (N - 1);          // partner Z(N - k) sits in the row of thread m % NBL
+                    const int qm = m % P::NBL, jm = m / P::NBL;
+                    const cplx Zm = buf[(qm % P::R1) * (P::M1 + 1) + (qm / P::R1) * P::RL + jm];
                     cplx A, B;
-                    unpack_pair(z[k], z[(N - k) & (N - 1)], A, B);
+                    unpack_pair(v[j], Zm, A, B);
                     ra[k] = A;
                     rb[k] = B;
                 }

@@ -113,7 +113,11 @@ struct nsb200_ctx {
     int device = 0, rank = 0, nranks = 1;
     int nx_loc = 0, x_start = 0, ny_loc = 0;
     double nu = 0, visc_pow = 1;
-    int system = 0, dealias = 1, kmax2 = 0;
+    int system = 0, dealias = 1, kmax2 = 0, kmax = 0;
+    int nzc = 0;                   // compact row stride of the workspace when kz <= kmax only is carried
+    bool prune = true;             // use the dealias support windows (NSB200_NO_PRUNE=1 disables)
+    bool u_in_window = false;      // resident state known to vanish outside the cube |k|_inf <= kmax
+    int* flag_dev = nullptr;
     size_t field_elems = 0;        // complex elements per planar local field
     cplx* slab = nullptr;          // one allocation for all fields
     cplx *U[3], *TMP[3], *ACC[3], *W[6], *R[6];
@@ -139,7 +143,7 @@ struct nsb200_ctx {
     struct ProfRec { int cls; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
-    Geom geom() const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.x_start = x_start; return g; }
+    Geom geom(bool windowed = false) const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.x_start = x_start; g.kcut = windowed ? kmax : N; return g; }
     long long nrows() const { return (long long)nx_loc * N; }
     int row_grid() const { long long r = nrows(); long long cap = (long long)sm_count * 32; return (int)(r < cap ? r : cap); }
 };
@@ -169,55 +173,79 @@ struct ProfScope {
 // One strided c2c pass.  axis 'y': Fourier slab [kx_loc][ky][kz], outer = kx_loc.  axis 'x': after the slab
 // exchange [kx][y_loc][kz], outer = y_loc.  `exch` selects the all-to-all block layout on the output
 // ('o', inverse y pass) or input ('i', forward y pass) side: element n of the transformed axis lives
-// at (n / ny_loc) * block + (n % ny_loc) * nzp, i.e. one contiguous block per destination rank.
-static int run_pass(nsb200_ctx* h, char axis, int dir, int nfields, cplx* const* src, cplx* const* dst, char exch,
-                    int field0 = 0, int field_cnt = -1) {
+// at (n / ny_loc) * block + (n % ny_loc) * rs, i.e. one contiguous block per destination rank.
+// Windows (exact, see DESIGN.md "dealias support pruning"): `in_w` = the input is known to vanish for
+// transformed-axis wavenumbers |k| > kmax (not loaded); `out_w` = outputs with |k| > kmax are not stored
+// (the dealias mask zeroes them); `outer_w` = pencils whose outer wavenumber is > kmax are skipped;
+// nzv = number of kz columns carried.
+struct PassSpec {
+    char axis; int dir; char exch;
+    int in_rs, out_rs;       // row strides (complex elements) of source / destination
+    int nzv;
+    bool in_w, out_w, outer_w;
+};
+static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* const* dst, int field0, int field_cnt) {
     StridedArgs a;
     memset(&a, 0, sizeof a);
-    if (field_cnt < 0) field_cnt = nfields;
     for (int f = 0; f < field_cnt; ++f) { a.src[f] = src[field0 + f]; a.dst[f] = dst[field0 + f]; }
     a.tw = h->tw;
-    a.nzv = h->nzf;
+    a.nzv = ps.nzv;
+    const int N = h->N, K = h->kmax;
+    a.in_zero_lo = ps.in_w ? K + 1 : N;  a.in_zero_hi = ps.in_w ? N - K : N;
+    a.out_skip_lo = ps.out_w ? K + 1 : N; a.out_skip_hi = ps.out_w ? N - K : N;
     a.outer_lo = a.outer_hi = 0;
-    a.in_zero_lo = a.in_zero_hi = h->N;
-    a.out_skip_lo = a.out_skip_hi = h->N;
-    const long long nzp = h->nzp;
     int n_outer;
     a.in_shift = a.out_shift = 30; a.in_mask = a.out_mask = 0x3fffffff; a.in_s1 = a.out_s1 = 0;
-    if (axis == 'y') {
+    if (ps.axis == 'y') {
         n_outer = h->nx_loc;
-        a.in_so = a.out_so = (long long)h->N * nzp;
-        a.in_s2 = a.out_s2 = nzp;
-        if (h->nranks > 1 && exch != 'n') {
+        if (ps.outer_w) {   // local kx planes with global index in [K+1, N-K) carry nothing
+            int lo = K + 1 - h->x_start, hi = N - K - h->x_start;
+            lo = lo < 0 ? 0 : (lo > h->nx_loc ? h->nx_loc : lo);
+            hi = hi < 0 ? 0 : (hi > h->nx_loc ? h->nx_loc : hi);
+            if (hi > lo) { a.outer_lo = lo; a.outer_hi = hi; n_outer -= hi - lo; }
+        }
+        a.in_so = (long long)N * ps.in_rs;  a.in_s2 = ps.in_rs;
+        a.out_so = (long long)N * ps.out_rs; a.out_s2 = ps.out_rs;
+        if (h->nranks > 1 && ps.exch != 'n') {
             int sh = 0;
             while ((1 << sh) < h->ny_loc) ++sh;
-            const long long block = (long long)h->nx_loc * h->ny_loc * nzp;
-            if (exch == 'o') { a.out_shift = sh; a.out_mask = h->ny_loc - 1; a.out_s1 = block; a.out_so = (long long)h->ny_loc * nzp; }
-            else { a.in_shift = sh; a.in_mask = h->ny_loc - 1; a.in_s1 = block; a.in_so = (long long)h->ny_loc * nzp; }
+            if (ps.exch == 'o') {
+                a.out_shift = sh; a.out_mask = h->ny_loc - 1;
+                a.out_s1 = (long long)h->nx_loc * h->ny_loc * ps.out_rs; a.out_so = (long long)h->ny_loc * ps.out_rs;
+            } else {
+                a.in_shift = sh; a.in_mask = h->ny_loc - 1;
+                a.in_s1 = (long long)h->nx_loc * h->ny_loc * ps.in_rs; a.in_so = (long long)h->ny_loc * ps.in_rs;
+            }
         }
     } else {
         n_outer = h->ny_loc;
-        a.in_so = a.out_so = nzp;
-        a.in_s2 = a.out_s2 = (long long)h->ny_loc * nzp;
+        a.in_so = ps.in_rs;  a.in_s2 = (long long)h->ny_loc * ps.in_rs;
+        a.out_so = ps.out_rs; a.out_s2 = (long long)h->ny_loc * ps.out_rs;
     }
     {
-        ProfScope ps(h, axis == 'y' ? (dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD));
-        CKI(h->ops->strided(dir, &a, n_outer, field_cnt, h->stream));
+        ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD));
+        CKI(h->ops->strided(ps.dir, &a, n_outer, field_cnt, h->stream));
     }
     h->launches++;
     return 0;
 }
+// full-spectrum pass on fields with the natural row stride nzp (3-D transform API, initial conditions)
+static int run_pass_full(nsb200_ctx* h, char axis, int dir, int nfields, cplx* const* src, cplx* const* dst) {
+    PassSpec ps = {axis, dir, 'n', h->nzp, h->nzp, h->nzf, false, false, false};
+    return run_pass(h, ps, src, dst, 0, nfields);
+}
 
-static int run_z(nsb200_ctx* h, int which, int nfields, cplx* const* f) {
+static int run_z(nsb200_ctx* h, int which, int nfields, cplx* const* f, int rs, int kz_in, int kz_out) {
     ZArgs a;
     memset(&a, 0, sizeof a);
     for (int i = 0; i < (which == NSB_Z_FUSED ? 6 : nfields); ++i) a.f[i] = f[i];
     a.tw = h->tw;
-    a.rs = h->nzp;
+    a.rs = rs;
     a.npairs = (long long)h->N * h->ny_loc / 2;
-    a.kz_in = h->nzf;
-    a.kz_out = h->nzf;
-    long long want = (a.npairs + h->ops->z_pairs_per_cta - 1) / h->ops->z_pairs_per_cta;
+    a.kz_in = kz_in;
+    a.kz_out = kz_out;
+    const int gpc = h->ops->z_pairs_per_cta[which];
+    long long want = (a.npairs + gpc - 1) / gpc;
     int grid = (int)(want < h->zgrid[which] ? want : h->zgrid[which]);
     {
         ProfScope ps(h, which == NSB_Z_FUSED ? NSB200_PC_Z_FUSED : which == NSB_Z_C2R ? NSB200_PC_Z_C2R : NSB200_PC_Z_R2C);
@@ -228,8 +256,8 @@ static int run_z(nsb200_ctx* h, int which, int nfields, cplx* const* f) {
 }
 
 // Slab all-to-all of `cnt` fields starting at field0: block s of every field goes to rank s.
-static int exchange(nsb200_ctx* h, cplx* const* send, cplx* const* recv, int field0, int cnt, cudaStream_t s) {
-    const size_t block = (size_t)h->nx_loc * h->ny_loc * h->nzp;   // complex elements
+static int exchange(nsb200_ctx* h, cplx* const* send, cplx* const* recv, int field0, int cnt, int rs, cudaStream_t s) {
+    const size_t block = (size_t)h->nx_loc * h->ny_loc * rs;   // complex elements
     CKN(g_nccl.GroupStart());
     for (int f = field0; f < field0 + cnt; ++f)
         for (int p = 0; p < h->nranks; ++p) {
@@ -240,13 +268,24 @@ static int exchange(nsb200_ctx* h, cplx* const* send, cplx* const* recv, int fie
     return 0;
 }
 
-// NonlinearRHSBatch up to (not including) normalise/project/dealias: raw (u x w)^ of `in` left in R[0..2].
-// solver.c:637-683.  Multi-rank: per-field pipelining of y pass -> all-to-all -> x pass over two streams.
-static int rhs_raw(nsb200_ctx* h, cplx* const* in) {
+// NonlinearRHSBatch up to (not including) normalise/project/dealias: raw (u x w)^ of `in` left in R[0..2]
+// (row stride returned in *c_rs).  solver.c:637-683.  in_w: `in` is known to vanish outside the dealias
+// cube, so the inverse transforms skip those modes.  The forward transforms skip the modes the dealias
+// mask will zero whenever dealiasing is on.  Multi-rank: per-field pipelining of y pass -> all-to-all ->
+// x pass over two streams.
+static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs) {
+    const bool out_w = h->prune && h->dealias == NSB200_DEALIAS_23;
+    in_w = in_w && h->prune;
+    // workspace row stride: compact when both directions carry kz <= kmax only
+    const int rs = (in_w && out_w) ? h->nzc : h->nzp;
+    const int nz_in = in_w ? h->kmax + 1 : h->nzf;
+    const int nz_out = out_w ? h->kmax + 1 : h->nzf;
+    *c_rs = rs;
     const int rg = h->row_grid();
     CurlArgs ca;
     for (int d = 0; d < 3; ++d) { ca.u[d] = in[d]; ca.w[d] = h->R[3 + d]; }
-    ca.g = h->geom();
+    ca.g = h->geom(in_w);
+    ca.w_rs = rs;
     {
         ProfScope ps(h, NSB200_PC_CURL);
         k_curl<<<rg, 128, 0, h->stream>>>(ca);
@@ -254,45 +293,56 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in) {
     CK(cudaGetLastError());
     h->launches++;
     cplx* src[6] = {in[0], in[1], in[2], h->R[3], h->R[4], h->R[5]};
-    if (h->nranks == 1) {
-        CKR(run_pass(h, 'y', INV, 6, src, h->W, 'n'));
-        CKR(run_pass(h, 'x', INV, 6, h->W, h->W, 'n'));
-        CKR(run_z(h, NSB_Z_FUSED, 3, h->W));
-        CKR(run_pass(h, 'x', FWD, 3, h->W, h->W, 'n'));
-        CKR(run_pass(h, 'y', FWD, 3, h->W, h->R, 'n'));   // R aliases W when nranks == 1
+    const bool multi = h->nranks > 1;
+    //                axis dir  exch            in_rs    out_rs nzv     in_w   out_w  outer_w
+    PassSpec yinv_u = {'y', INV, multi ? 'o' : 'n', h->nzp, rs, nz_in, in_w, false, in_w};
+    PassSpec yinv_w = {'y', INV, multi ? 'o' : 'n', rs,     rs, nz_in, in_w, false, in_w};
+    PassSpec xinv   = {'x', INV, 'n',               rs,     rs, nz_in, in_w, false, false};
+    PassSpec xfwd   = {'x', FWD, 'n',               rs,     rs, nz_out, false, out_w, false};
+    PassSpec yfwd   = {'y', FWD, multi ? 'i' : 'n', rs,     rs, nz_out, false, out_w, out_w};
+    if (!multi) {
+        CKR(run_pass(h, yinv_u, src, h->W, 0, 3));
+        CKR(run_pass(h, yinv_w, src, h->W, 3, 3));
+        CKR(run_pass(h, xinv, h->W, h->W, 0, 6));
+        CKR(run_z(h, NSB_Z_FUSED, 3, h->W, rs, nz_in, nz_out));
+        CKR(run_pass(h, xfwd, h->W, h->W, 0, 3));
+        CKR(run_pass(h, yfwd, h->W, h->R, 0, 3));   // R aliases W when nranks == 1
         return 0;
     }
     // inverse: y pass (field f) | exchange (field f) | x pass (field f), pipelined across fields
     for (int f = 0; f < 6; ++f) {
-        CKR(run_pass(h, 'y', INV, 6, src, h->W, 'o', f, 1));
+        CKR(run_pass(h, f < 3 ? yinv_u : yinv_w, src, h->W, f, 1));
         CK(cudaEventRecord(h->ev_field[f], h->stream));
         CK(cudaStreamWaitEvent(h->comm_stream, h->ev_field[f], 0));
-        CKR(exchange(h, h->W, h->R, f, 1, h->comm_stream));
+        CKR(exchange(h, h->W, h->R, f, 1, rs, h->comm_stream));
         CK(cudaEventRecord(h->ev_comm[f], h->comm_stream));
     }
     for (int f = 0; f < 6; ++f) {
         CK(cudaStreamWaitEvent(h->stream, h->ev_comm[f], 0));
-        CKR(run_pass(h, 'x', INV, 6, h->R, h->R, 'n', f, 1));
+        CKR(run_pass(h, xinv, h->R, h->R, f, 1));
     }
-    CKR(run_z(h, NSB_Z_FUSED, 3, h->R));
+    CKR(run_z(h, NSB_Z_FUSED, 3, h->R, rs, nz_in, nz_out));
     for (int f = 0; f < 3; ++f) {
-        CKR(run_pass(h, 'x', FWD, 3, h->R, h->R, 'n', f, 1));
+        CKR(run_pass(h, xfwd, h->R, h->R, f, 1));
         CK(cudaEventRecord(h->ev_field[f], h->stream));
         CK(cudaStreamWaitEvent(h->comm_stream, h->ev_field[f], 0));
-        CKR(exchange(h, h->R, h->W, f, 1, h->comm_stream));
+        CKR(exchange(h, h->R, h->W, f, 1, rs, h->comm_stream));
         CK(cudaEventRecord(h->ev_comm[f], h->comm_stream));
     }
     // the forward y pass writes R[0..2] (natural order): all exchanges out of R must be complete
     for (int f = 0; f < 3; ++f) CK(cudaStreamWaitEvent(h->stream, h->ev_comm[f], 0));
-    CKR(run_pass(h, 'y', FWD, 3, h->W, h->R, 'i'));
+    CKR(run_pass(h, yfwd, h->W, h->R, 0, 3));
     return 0;
 }
 
-static int rk_stage(nsb200_ctx* h, int stage, double dt) {
+static int rk_stage(nsb200_ctx* h, int stage, double dt, int c_rs, bool in_w) {
     RkArgs a;
     memset(&a, 0, sizeof a);
     for (int d = 0; d < 3; ++d) { a.c[d] = h->R[d]; a.u[d] = h->U[d]; a.tmp[d] = h->TMP[d]; a.acc[d] = h->ACC[d]; a.uout[d] = h->U[d]; }
-    a.g = h->geom();
+    const bool out_w = h->prune && h->dealias == NSB200_DEALIAS_23;
+    a.g = h->geom(out_w);
+    a.c_rs = c_rs;
+    a.skip_outside = (out_w && in_w && h->prune && stage != 4) ? 1 : 0;
     a.stage = stage;
     a.dealias = h->dealias;
     a.kmax2 = h->kmax2;
@@ -311,24 +361,48 @@ static int rk_stage(nsb200_ctx* h, int stage, double dt) {
 }
 
 static int step(nsb200_ctx* h, double dt) {
-    CKR(rhs_raw(h, h->U));   CKR(rk_stage(h, 0, dt));   // solver.c:522-536
-    CKR(rhs_raw(h, h->TMP)); CKR(rk_stage(h, 1, dt));   // :538-552
-    CKR(rhs_raw(h, h->TMP)); CKR(rk_stage(h, 2, dt));   // :554-568
-    CKR(rhs_raw(h, h->TMP)); CKR(rk_stage(h, 3, dt));   // :570-607
+    // U (and hence every stage input U + a dt k_i) stays inside the dealias cube once it is there
+    const bool w = h->u_in_window && h->dealias == NSB200_DEALIAS_23;
+    int crs = 0;
+    CKR(rhs_raw(h, h->U, w, &crs));   CKR(rk_stage(h, 0, dt, crs, w));   // solver.c:522-536
+    CKR(rhs_raw(h, h->TMP, w, &crs)); CKR(rk_stage(h, 1, dt, crs, w));   // :538-552
+    CKR(rhs_raw(h, h->TMP, w, &crs)); CKR(rk_stage(h, 2, dt, crs, w));   // :554-568
+    CKR(rhs_raw(h, h->TMP, w, &crs)); CKR(rk_stage(h, 3, dt, crs, w));   // :570-607
+    return 0;
+}
+
+// does the resident state vanish outside the dealias cube?  (decides whether pruning is exact)
+static int check_state_support(nsb200_ctx* h) {
+    h->u_in_window = false;
+    if (h->dealias != NSB200_DEALIAS_23) return 0;
+    CK(cudaMemsetAsync(h->flag_dev, 0, sizeof(int), h->stream));
+    k_check_support<<<h->row_grid(), 128, 0, h->stream>>>(h->U[0], h->U[1], h->U[2], h->geom(), h->kmax, h->flag_dev);
+    CK(cudaGetLastError());
+    h->launches++;
+    int flag = 1;
+    CK(cudaMemcpyAsync(&flag, h->flag_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->nranks > 1) {   // every rank must take the same path
+        CK(cudaMemcpyAsync(h->flag_dev, &flag, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CKN(g_nccl.AllReduce(h->flag_dev, h->flag_dev, 1, ncclInt32, ncclMax, h->comm, h->stream));
+        CK(cudaMemcpyAsync(&flag, h->flag_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->u_in_window = (flag == 0);
     return 0;
 }
 
 // forward / inverse 3-D transforms of 3 planar fields held in W (single rank), real <-> half complex in place
 static int fft3_r2c_inplace(nsb200_ctx* h) {
-    CKR(run_z(h, NSB_Z_R2C, 3, h->W));
-    CKR(run_pass(h, 'x', FWD, 3, h->W, h->W, 'n'));
-    CKR(run_pass(h, 'y', FWD, 3, h->W, h->W, 'n'));
+    CKR(run_z(h, NSB_Z_R2C, 3, h->W, h->nzp, h->nzf, h->nzf));
+    CKR(run_pass_full(h, 'x', FWD, 3, h->W, h->W));
+    CKR(run_pass_full(h, 'y', FWD, 3, h->W, h->W));
     return 0;
 }
 static int fft3_c2r_inplace(nsb200_ctx* h) {
-    CKR(run_pass(h, 'y', INV, 3, h->W, h->W, 'n'));
-    CKR(run_pass(h, 'x', INV, 3, h->W, h->W, 'n'));
-    CKR(run_z(h, NSB_Z_C2R, 3, h->W));
+    CKR(run_pass_full(h, 'y', INV, 3, h->W, h->W));
+    CKR(run_pass_full(h, 'x', INV, 3, h->W, h->W));
+    CKR(run_z(h, NSB_Z_C2R, 3, h->W, h->nzp, h->nzf, h->nzf));
     return 0;
 }
 
@@ -352,7 +426,7 @@ int nsb200_destroy(nsb200_ctx* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     if (h->comm) g_nccl.CommDestroy(h->comm);
-    cudaFree(h->slab); cudaFree(h->tw); cudaFree(h->meas_partial); cudaFree(h->meas_dev); cudaFree(h->spect_dev);
+    cudaFree(h->slab); cudaFree(h->tw); cudaFree(h->meas_partial); cudaFree(h->meas_dev); cudaFree(h->spect_dev); cudaFree(h->flag_dev);
     cudaFree(h->flush_buf);
     if (h->meas_host) cudaFreeHost(h->meas_host);
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -390,6 +464,9 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     h->nu = nu; h->visc_pow = visc_pow; h->system = system; h->dealias = dealias_mode;
     const int kmax = h->N / 3;   // integer division, solver.c:1732
     h->kmax2 = kmax * kmax;
+    h->kmax = kmax;
+    h->nzc = (kmax + 1 + 7) / 8 * 8;
+    { const char* e = getenv("NSB200_NO_PRUNE"); h->prune = !(e && e[0] == '1'); }
     h->ops = ops;
     h->field_elems = (size_t)h->nx_loc * h->N * h->nzp;
 #define CKC(call)                                                                                    \
@@ -443,6 +520,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     h->meas_grid = (int)std::min<long long>(h->nrows(), (long long)h->sm_count * 8);
     CKC(cudaMalloc(&h->meas_partial, sizeof(double) * NSB_NMEAS * h->meas_grid));
     CKC(cudaMalloc(&h->meas_dev, sizeof(double) * NSB_NMEAS));
+    CKC(cudaMalloc(&h->flag_dev, sizeof(int)));
     CKC(cudaMalloc(&h->spect_dev, sizeof(double) * 2 * 2048));
     CKC(cudaMallocHost(&h->meas_host, sizeof(double) * 2 * 2048));
     {
@@ -501,6 +579,7 @@ int nsb200_upload_uhat(nsb200_ctx* h, const double* u_hat_host) {
     if (!h || !u_hat_host) return fail("nsb200_upload_uhat: null argument");
     CKR(set_device(h));
     CKR(upload_to(h, u_hat_host, h->U));
+    CKR(check_state_support(h));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -526,8 +605,9 @@ int nsb200_nonlinear_rhs(nsb200_ctx* h, const double* u_hat_in, double* dw_hat_d
     if (!h || !u_hat_in || !dw_hat_dt_out) return fail("nsb200_nonlinear_rhs: null argument");
     CKR(set_device(h));
     CKR(upload_to(h, u_hat_in, h->TMP));
-    CKR(rhs_raw(h, h->TMP));
-    CKR(rk_stage(h, 4, 0.0));   // normalise + project + dealias -> ACC
+    int crs = 0;
+    CKR(rhs_raw(h, h->TMP, false, &crs));   // arbitrary input: no assumption on its support
+    CKR(rk_stage(h, 4, 0.0, crs, false));   // normalise + project + dealias -> ACC
     return download_from(h, dw_hat_dt_out, h->ACC);
 }
 
@@ -662,6 +742,7 @@ int nsb200_initial_condition(nsb200_ctx* h, const char* name, unsigned long long
         CK(cudaGetLastError());
         h->launches++;
     }
+    CKR(check_state_support(h));
     if (!strcmp(name, "RANDOM_PHASE") && energy > 0.0) {
         double p[NSB_NMEAS], v[5];
         CKR(nsb200_measure(h, p));
@@ -746,11 +827,11 @@ int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_
         switch (op) {
             case NSB200_OP_RK4_STEP: CKR(step(h, dt)); break;
             case NSB200_OP_FFT_C2R_R2C: CKR(fft3_c2r_inplace(h)); CKR(fft3_r2c_inplace(h)); break;
-            case NSB200_OP_PASS_Y: CKR(run_pass(h, 'y', INV, 3, h->W, h->W, 'n')); break;
-            case NSB200_OP_PASS_X: CKR(run_pass(h, 'x', INV, 3, h->W, h->W, 'n')); break;
-            case NSB200_OP_PASS_Z: CKR(run_z(h, NSB_Z_C2R, 3, h->W)); break;
-            case NSB200_OP_Z_FUSED: CKR(run_z(h, NSB_Z_FUSED, 3, h->W)); break;
-            case NSB200_OP_RK_POINTWISE: CKR(rk_stage(h, 1, dt)); break;
+            case NSB200_OP_PASS_Y: CKR(run_pass_full(h, 'y', INV, 3, h->W, h->W)); break;
+            case NSB200_OP_PASS_X: CKR(run_pass_full(h, 'x', INV, 3, h->W, h->W)); break;
+            case NSB200_OP_PASS_Z: CKR(run_z(h, NSB_Z_C2R, 3, h->W, h->nzp, h->nzf, h->nzf)); break;
+            case NSB200_OP_Z_FUSED: CKR(run_z(h, NSB_Z_FUSED, 3, h->W, h->nzp, h->nzf, h->nzf)); break;
+            case NSB200_OP_RK_POINTWISE: CKR(rk_stage(h, 1, dt, h->nzp, false)); break;
             case NSB200_OP_L2_FLUSH: CK(cudaMemsetAsync(h->flush_buf, it & 0xff, h->flush_bytes, h->stream)); break;
             default: return fail("nsb200_time_op: unknown op");
         }

@@ -14,7 +14,11 @@ struct Geom {
     int nzp;      // row stride (complex elements) of the planar device fields
     int nx_loc;   // local number of kx planes (slab)
     int x_start;  // global index of the first local kx plane
+    int kcut;     // support window: only |kx|, |ky| <= kcut and kz <= kcut are touched (kcut >= N: everything)
 };
+
+NSB_HD bool nsb_in_window(int kx, int ky, int kcut) { return kx <= kcut && -kx <= kcut && ky <= kcut && -ky <= kcut; }
+NSB_HD int nsb_kz_count(const Geom& g) { return g.kcut + 1 < g.nzf ? g.kcut + 1 : g.nzf; }
 
 NSB_HD int nsb_wavenum(int idx, int N) { return idx <= N / 2 ? idx : idx - N; }  // solver.c:1793,1807
 
@@ -82,6 +86,7 @@ struct CurlArgs {
     const cplx* u[3];
     cplx* w[3];
     Geom g;
+    int w_rs;   // row stride of w (complex elements)
 };
 __global__ void k_curl(const CurlArgs a) {
     const Geom g = a.g;
@@ -89,13 +94,15 @@ __global__ void k_curl(const CurlArgs a) {
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
         const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
-        const long long base = row * g.nzp;
-        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+        if (!nsb_in_window(kx, ky, g.kcut)) continue;
+        const long long base = row * g.nzp, wbase = row * a.w_rs;
+        const int nk = nsb_kz_count(g);
+        for (int k = threadIdx.x; k < nk; k += blockDim.x) {
             cplx wx, wy, wz;
             curl_mode(kx, ky, k, a.u[0][base + k], a.u[1][base + k], a.u[2][base + k], wx, wy, wz);
-            a.w[0][base + k] = wx;
-            a.w[1][base + k] = wy;
-            a.w[2][base + k] = wz;
+            a.w[0][wbase + k] = wx;
+            a.w[1][wbase + k] = wy;
+            a.w[2][wbase + k] = wz;
         }
     }
 }
@@ -113,6 +120,8 @@ struct RkArgs {
     int kmax2;           // (N/3)^2
     int euler;           // __EULER update (solver.c:585) instead of the viscous factor (:601)
     int hyper2;          // visc_pow == 2 (pow(k_sqr, 2.0), solver.c:594)
+    int c_rs;            // row stride of c (complex elements)
+    int skip_outside;    // modes outside the support window are exact zeros in u/tmp/acc: leave them alone
     double dt, nu, visc_pow, norm;
 };
 
@@ -146,10 +155,17 @@ __global__ void k_rk_stage(const RkArgs a) {
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
         const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
-        const long long base = row * g.nzp;
-        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+        const long long base = row * g.nzp, cbase = row * a.c_rs;
+        const bool row_in = nsb_in_window(kx, ky, g.kcut);
+        if (!row_in && a.skip_outside) continue;
+        const int nk = a.skip_outside ? nsb_kz_count(g) : g.nzf;
+        for (int k = threadIdx.x; k < nk; k += blockDim.x) {
             const long long e = base + k;
-            cplx c[3] = {a.c[0][e], a.c[1][e], a.c[2][e]};
+            // outside the window the forward transform was not stored: the dealias mask makes it zero
+            const bool in = row_in && k <= g.kcut;
+            cplx c[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) c[d] = in ? a.c[d][cbase + k] : mk(0.0, 0.0);
             project_mode(kx, ky, k, a.norm, a.dealias, a.kmax2, c[0], c[1], c[2]);
             if (a.stage == 4) {
 #pragma unroll
@@ -223,6 +239,25 @@ __global__ void k_scale_planar(cplx* p0, cplx* p1, cplx* p2, Geom g, double s) {
             const long long e = row * g.nzp + k;
             p0[e] = cscale(p0[e], s); p1[e] = cscale(p1[e], s); p2[e] = cscale(p2[e], s);
         }
+}
+
+// sets *flag when any mode outside the cube |kx|,|ky|,kz <= kcut is non-zero (decides whether the pruned
+// transforms may be used for an uploaded state)
+__global__ void k_check_support(const cplx* p0, const cplx* p1, const cplx* p2, Geom g, int kcut, int* flag) {
+    const long long nrows = (long long)g.nx_loc * g.N;
+    int bad = 0;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const bool row_in = nsb_in_window(kx, ky, kcut);
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            if (row_in && k <= kcut) continue;
+            const long long e = row * g.nzp + k;
+            const cplx a = p0[e], b = p1[e], c = p2[e];
+            if (a.x != 0.0 || a.y != 0.0 || b.x != 0.0 || b.y != 0.0 || c.x != 0.0 || c.y != 0.0) bad = 1;
+        }
+    }
+    if (bad) atomicOr(flag, 1);
 }
 
 // ------------------------------------------------------------------------------ diagnostics

@@ -6,7 +6,7 @@
 #include <cmath>
 #include <vector>
 #include <cstdlib>
-#include "../../3d_navier_stokes_b200/csrc/fft_core.cuh"
+#include "../../3d_navier_stokes_b200/csrc/fft_kernels.cuh"
 
 static double frand() { return (double)rand() / RAND_MAX - 0.5; }
 
@@ -93,6 +93,95 @@ template <int N> int check_pack() {
     return (err / N < 5e-15 && err2 < 5e-15) ? 0 : 1;
 }
 
+// Emulates k_z_fused's data flow for one pencil pair (teams, in-place rows, partner look-up) and checks
+// it against the straightforward formulation: c2r of six half spectra, u x w, r2c of the product.
+template <class P> int check_fused() {
+    constexpr int N = P::N, TP = P::NB1, NP = P::NPAD;
+    static_assert(P::R1 == P::RL, "balanced plan");
+    std::vector<cplx> tw(N), sm(6 * NP, mk(1e300, 1e300));
+    for (int m = 0; m < N; ++m) {
+        long double a = -2.0L * 3.14159265358979323846264338327950288L * m / N;
+        tw[m] = mk((double)cosl(a), (double)sinl(a));
+    }
+    std::vector<cplx> rows[6][2], outA[3], outB[3];
+    for (int f = 0; f < 6; ++f) for (int r = 0; r < 2; ++r) { rows[f][r].resize(N / 2 + 1); for (auto& z : rows[f][r]) z = mk(frand(), frand()); }
+    auto rowbase = [](int q) { return (q % P::R1) * (P::M1 + 1) + (q / P::R1) * P::RL; };
+    // inverse
+    for (int t = 0; t < 3; ++t) for (int ff = 0; ff < 2; ++ff) for (int q = 0; q < TP; ++q) {
+        int f = 2 * t + ff;
+        fft_pass1<P, INV, 1>(q, sm.data() + f * NP, tw.data(), [&](int n) { int k = n <= N / 2 ? n : N - n; return pack_hermitian<N>(n, rows[f][0][k], rows[f][1][k]); });
+    }
+    if constexpr (P::PASSES == 3)
+        for (int f = 0; f < 6; ++f) for (int b = 0; b < P::NB2; ++b) fft_pass2<P, INV, 1>(b, sm.data() + f * NP, tw.data());
+    for (int f = 0; f < 6; ++f) for (int q = 0; q < TP; ++q) {
+        cplx v[P::RL]; fft_pass_last<P, INV, 1>(q, sm.data() + f * NP, v);
+        for (int j = 0; j < P::RL; ++j) sm[f * NP + rowbase(q) + j] = v[j];
+    }
+    // reference real-space fields via naive c2r
+    std::vector<double> real[6][2];
+    for (int f = 0; f < 6; ++f) for (int r = 0; r < 2; ++r) {
+        real[f][r].resize(N);
+        for (int n = 0; n < N; ++n) {
+            long double sacc = 0;
+            for (int k = 0; k < N; ++k) {
+                int kk = k <= N / 2 ? k : N - k;
+                long double ar = rows[f][r][kk].x, ai = (k <= N / 2 ? rows[f][r][kk].y : -rows[f][r][kk].y);
+                if (k == 0 || k == N / 2) ai = 0;
+                long double a = 2.0L * 3.14159265358979323846264338327950288L * ((long long)n * k % N) / N;
+                sacc += ar * cosl(a) - ai * sinl(a);
+            }
+            real[f][r][n] = (double)sacc;
+        }
+    }
+    // product + forward pass 1 in registers, then scatter
+    std::vector<std::vector<cplx>> creg(3 * TP, std::vector<cplx>(P::R1));
+    for (int t = 0; t < 3; ++t) for (int q = 0; q < TP; ++q) {
+        int i1 = (t + 1) % 3, i2 = (t + 2) % 3;
+        cplx c[P::R1];
+        for (int j = 0; j < P::R1; ++j)
+            c[j] = cross_comp(sm[i1 * NP + rowbase(q) + j], sm[(3 + i2) * NP + rowbase(q) + j], sm[i2 * NP + rowbase(q) + j], sm[(3 + i1) * NP + rowbase(q) + j]);
+        fft_pass1_regs<P, FWD>(q, c, tw.data());
+        for (int j = 0; j < P::R1; ++j) creg[t * TP + q][j] = c[j];
+    }
+    for (int t = 0; t < 3; ++t) for (int q = 0; q < TP; ++q) fft_pass1_scatter<P, 1>(q, sm.data() + t * NP, creg[t * TP + q].data());
+    if constexpr (P::PASSES == 3)
+        for (int t = 0; t < 3; ++t) for (int b = 0; b < P::NB2; ++b) fft_pass2<P, FWD, 1>(b, sm.data() + t * NP, tw.data());
+    std::vector<std::vector<cplx>> vreg(3 * TP, std::vector<cplx>(P::RL));
+    for (int t = 0; t < 3; ++t) for (int q = 0; q < TP; ++q) {
+        cplx v[P::RL]; fft_pass_last<P, FWD, 1>(q, sm.data() + t * NP, v);
+        for (int j = 0; j < P::RL; ++j) vreg[t * TP + q][j] = v[j];
+    }
+    for (int t = 0; t < 3; ++t) for (int q = 0; q < TP; ++q) for (int j = 0; j < P::RL; ++j) sm[t * NP + rowbase(q) + j] = vreg[t * TP + q][j];
+    for (int t = 0; t < 3; ++t) { outA[t].assign(N / 2 + 1, mk(0, 0)); outB[t].assign(N / 2 + 1, mk(0, 0)); }
+    for (int t = 0; t < 3; ++t) for (int q = 0; q < TP; ++q) for (int j = 0; j <= P::RL / 2; ++j) {
+        int k = q + j * P::NBL;
+        if (k <= N / 2) {
+            int m = (N - k) & (N - 1), qm = m % P::NBL, jm = m / P::NBL;
+            cplx Zm = sm[t * NP + rowbase(qm) + jm];
+            unpack_pair(vreg[t * TP + q][j], Zm, outA[t][k], outB[t][k]);
+        }
+    }
+    // reference: r2c of the real-space product
+    double err = 0, nrm = 0;
+    for (int t = 0; t < 3; ++t) for (int r = 0; r < 2; ++r) {
+        int i1 = (t + 1) % 3, i2 = (t + 2) % 3;
+        std::vector<double> c(N);
+        for (int n = 0; n < N; ++n) c[n] = real[i1][r][n] * real[3 + i2][r][n] - real[i2][r][n] * real[3 + i1][r][n];
+        for (int k = 0; k <= N / 2; ++k) {
+            long double sr = 0, si = 0;
+            for (int n = 0; n < N; ++n) {
+                long double a = -2.0L * 3.14159265358979323846264338327950288L * ((long long)n * k % N) / N;
+                sr += c[n] * cosl(a); si += c[n] * sinl(a);
+            }
+            cplx got = r == 0 ? outA[t][k] : outB[t][k];
+            err = fmax(err, fmax(fabs(got.x - (double)sr), fabs(got.y - (double)si)));
+            nrm = fmax(nrm, fmax(fabs((double)sr), fabs((double)si)));
+        }
+    }
+    printf("fused N=%d (%d,%d,%d): max rel err %.3e\n", N, P::R1, P::R2, P::R3, err / nrm);
+    return err / nrm < 1e-13 ? 0 : 1;
+}
+
 int main() {
     int bad = 0;
     bad += check<BigPlan<16>::type>("big");
@@ -105,6 +194,16 @@ int main() {
     bad += check<ZPlan<64>::type>("z");
     bad += check<ZPlan<128>::type>("z");
     bad += check<ZPlan<256>::type>("z");
+    bad += check<ZFPlan<32>::type>("zf");
+    bad += check<ZFPlan<128>::type>("zf");
+    bad += check<ZFPlan<256>::type>("zf");
+    bad += check<ZFPlan<1024>::type>("zf");
+    bad += check_fused<ZFPlan<16>::type>();
+    bad += check_fused<ZFPlan<32>::type>();
+    bad += check_fused<ZFPlan<64>::type>();
+    bad += check_fused<ZFPlan<128>::type>();
+    bad += check_fused<ZFPlan<256>::type>();
+    bad += check_fused<ZFPlan<512>::type>();
     bad += check_pack<16>();
     bad += check_pack<64>();
     bad += check_pack<512>();
