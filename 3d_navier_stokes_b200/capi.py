@@ -46,7 +46,8 @@ OP_RK4_STEP, OP_FFT_C2R_R2C, OP_PASS_Y, OP_PASS_X, OP_PASS_Z, OP_L2_FLUSH, OP_Z_
 
 
 def lib_path():
-    return os.path.join(_HERE, "libnsb200.so")
+    # NSB200_LIB selects an alternative build of the same ABI (kernel tuning experiments)
+    return os.environ.get("NSB200_LIB") or os.path.join(_HERE, "libnsb200.so")
 
 
 class Lib:

@@ -208,6 +208,51 @@ NSB_HD void fft_pass2(int b, cplx* sm, const cplx* __restrict__ tw) {
     for (int kp = 0; kp < P::R2; ++kp) sm[(base + kp * P::R3) * STRIDE] = v[kp];
 }
 
+// ---- passes with the (loop invariant) twiddles of this thread held in registers
+// pass 1 twiddles of butterfly b: W_N^{b k1}, k1 = 1..R1-1  (stored forward; conjugated on use for INV)
+template <class P> NSB_HD void load_tw_pass1(int b, const cplx* __restrict__ tw, cplx* w) {
+#pragma unroll
+    for (int k1 = 1; k1 < P::R1; ++k1) w[k1 - 1] = tw[b * k1];
+}
+// pass 2 twiddles of butterfly b: W_N^{R1 (b % R3) kp}, kp = 1..R2-1
+template <class P> NSB_HD void load_tw_pass2(int b, const cplx* __restrict__ tw, cplx* w) {
+#pragma unroll
+    for (int kp = 1; kp < P::R2; ++kp) w[kp - 1] = tw[P::R1 * (b % P::R3) * kp];
+}
+template <int DIR> NSB_HD cplx cmul_dir(cplx a, cplx w) {   // a * w (FWD) or a * conj(w) (INV)
+    return DIR == FWD ? mk(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x) : mk(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+}
+template <class P, int DIR, int STRIDE, class Ld>
+NSB_HD void fft_pass1_rw(int b, cplx* sm, const cplx* w, Ld ld) {
+    cplx v[P::R1];
+#pragma unroll
+    for (int j = 0; j < P::R1; ++j) v[j] = ld(b + j * P::M1);
+    Dft<P::R1, DIR>::run(v);
+#pragma unroll
+    for (int k1 = 1; k1 < P::R1; ++k1) v[k1] = cmul_dir<DIR>(v[k1], w[k1 - 1]);
+#pragma unroll
+    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * (P::M1 + 1) + b) * STRIDE] = v[k1];
+}
+template <class P, int DIR> NSB_HD void fft_pass1_regs_rw(cplx* v, const cplx* w) {
+    Dft<P::R1, DIR>::run(v);
+#pragma unroll
+    for (int k1 = 1; k1 < P::R1; ++k1) v[k1] = cmul_dir<DIR>(v[k1], w[k1 - 1]);
+}
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass2_rw(int b, cplx* sm, const cplx* w) {
+    static_assert(P::PASSES == 3, "pass2 only exists in 3-pass plans");
+    const int k1 = b / P::R3, m2 = b % P::R3;
+    const int base = k1 * (P::M1 + 1) + m2;
+    cplx v[P::R2];
+#pragma unroll
+    for (int j = 0; j < P::R2; ++j) v[j] = sm[(base + j * P::R3) * STRIDE];
+    Dft<P::R2, DIR>::run(v);
+#pragma unroll
+    for (int kp = 1; kp < P::R2; ++kp) v[kp] = cmul_dir<DIR>(v[kp], w[kp - 1]);
+#pragma unroll
+    for (int kp = 0; kp < P::R2; ++kp) sm[(base + kp * P::R3) * STRIDE] = v[kp];
+}
+
 // last pass: v[k2] is output element  b + k2 * P::NBL
 template <class P, int DIR, int STRIDE>
 NSB_HD void fft_pass_last(int b, const cplx* sm, cplx* v) {

@@ -23,6 +23,15 @@
 #define NSB_DIV(a, b) ((a) / (b))
 #endif
 
+// Field data is streamed once per pass: load it with ld.global.cg (L2 only) so that the small L1 left
+// beside the shared-memory carve-out keeps the twiddle table resident (ncu: with default caching the
+// table was evicted and ~2/3 of all L1 global-load sectors were twiddle re-fetches from L2).
+#ifdef __CUDA_ARCH__
+#define NSB_LDCG(p) __ldcg(p)
+#else
+#define NSB_LDCG(p) (*(p))
+#endif
+
 #define NSB_MAX_FIELDS 6
 
 // ------------------------------------------------------------------------------ strided c2c pass
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a) {
 
     for (int b = q; b < P::NB1; b += TP) {
         fft_pass1<P, DIR, T>(b, sm, tw, [&](int n) {
-            return (valid && !(n >= zlo && n < zhi)) ? src[(long long)(n >> ish) * is1 + (long long)(n & imk) * is2] : mk(0.0, 0.0);
+            return (valid && !(n >= zlo && n < zhi)) ? NSB_LDCG(src + ((long long)(n >> ish) * is1 + (long long)(n & imk) * is2)) : mk(0.0, 0.0);
         });
     }
     __syncthreads();
@@ -91,7 +100,8 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a) {
 
 // ------------------------------------------------------------------------------ z pencils
 struct ZArgs {
-    cplx* f[NSB_MAX_FIELDS];   // planar fields, rows of `rs` complex ( = 2*rs doubles when real)
+    cplx* base;                // field f starts at base + f * fstride; rows of `rs` complex (= 2*rs doubles when real)
+    long long fstride;         // (a pointer array indexed at run time would be copied to local memory)
     const cplx* tw;
     long long rs;              // row stride in complex elements
     long long npairs;          // row pairs per field
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(ZCfg<P>::THREADS) k_z_c2r(const ZArgs a) {
     cplx* smem = reinterpret_cast<cplx*>(nsb_smem_raw);
     const int s = threadIdx.x / TP, q = threadIdx.x % TP;
     cplx* sm = smem + s * P::NPAD;
-    cplx* F = a.f[blockIdx.y];
+    cplx* F = a.base + (long long)blockIdx.y * a.fstride;
     const cplx* __restrict__ tw = a.tw;
     const int kzin = a.kz_in;
     for (long long pr0 = (long long)blockIdx.x * G; pr0 < a.npairs; pr0 += (long long)gridDim.x * G) {
@@ -124,7 +134,7 @@ __global__ void __launch_bounds__(ZCfg<P>::THREADS) k_z_c2r(const ZArgs a) {
             fft_pass1<P, INV, 1>(q, sm, tw, [&](int n) {
                 const int k = (n <= N / 2) ? n : N - n;
                 if (k >= kzin) return mk(0.0, 0.0);
-                return pack_hermitian<N>(n, ra[k], rb[k]);
+                return pack_hermitian<N>(n, NSB_LDCG(ra + k), NSB_LDCG(rb + k));
             });
         }
         __syncthreads();
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(ZCfg<P>::THREADS) k_z_r2c(const ZArgs a) {
     cplx* smem = reinterpret_cast<cplx*>(nsb_smem_raw);
     const int s = threadIdx.x / TP, q = threadIdx.x % TP;
     cplx* sm = smem + s * P::NPAD;
-    cplx* F = a.f[blockIdx.y];
+    cplx* F = a.base + (long long)blockIdx.y * a.fstride;
     const cplx* __restrict__ tw = a.tw;
     const int kzout = a.kz_out;
     for (long long pr0 = (long long)blockIdx.x * G; pr0 < a.npairs; pr0 += (long long)gridDim.x * G) {
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(ZCfg<P>::THREADS) k_z_r2c(const ZArgs a) {
         if (ok) {
             const double* ia = reinterpret_cast<const double*>(ra);
             const double* ib = reinterpret_cast<const double*>(rb);
-            fft_pass1<P, FWD, 1>(q, sm, tw, [&](int n) { return mk(ia[n], ib[n]); });
+            fft_pass1<P, FWD, 1>(q, sm, tw, [&](int n) { return mk(NSB_LDCG(ia + n), NSB_LDCG(ib + n)); });
         }
         __syncthreads();
         if constexpr (P::PASSES == 3) {
@@ -207,6 +217,9 @@ NSB_HD cplx cross_comp(cplx a1, cplx b2, cplx a2, cplx b1) {
 // last inverse pass is the one that consumes them in the first forward pass: the last inverse pass
 // writes its outputs back IN PLACE (its own shared-memory row), no natural-order shuffle is needed and
 // the six real-space fields of the pair never leave the SM.
+#ifndef NSB_ZF_MIN_REGS
+#define NSB_ZF_MIN_REGS 104
+#endif
 template <class P> struct ZFusedCfg {
     static_assert(P::R1 == P::RL, "fused z kernel needs a balanced plan (first radix == last radix)");
     static constexpr int TP = P::NB1;
@@ -214,10 +227,10 @@ template <class P> struct ZFusedCfg {
     static constexpr int G = (TEAM >= 96) ? 1 : (96 / TEAM);
     static constexpr int THREADS = TEAM * G;
     // resident CTAs per SM the register allocation must allow: as many as shared memory admits, capped so
-    // that a thread keeps >= 80 registers
+    // that a thread keeps >= NSB_ZF_MIN_REGS registers (80 spilled 260 B/thread to L2: see profiles/)
     static constexpr int SMEM = 6 * P::NPAD * G * 16;
     static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
-    static constexpr int BY_REGS = 65536 / (THREADS * 80);
+    static constexpr int BY_REGS = 65536 / (THREADS * NSB_ZF_MIN_REGS);
     static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
 };
 
@@ -234,35 +247,44 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
     const int kzin = a.kz_in, kzout = a.kz_out;
     // this thread's row in the in-place layout (same indexing as fft_pass_last with b = q)
     const int rowbase = (q % P::R1) * (P::M1 + 1) + (q / P::R1) * P::RL;
+    // Loop-invariant twiddles of this thread live in registers: in this kernel every lane needs different
+    // table entries, so fetching them per pass cost more L1 cycles than the data exchange (profiles/).
+    constexpr bool RW2 = (P::PASSES == 3) && (P::NB2 == TP);   // one pass-2 butterfly per thread
+    cplx tw1[P::R1 - 1];
+    cplx tw2[RW2 ? P::R2 - 1 : 1];
+    load_tw_pass1<P>(q, tw, tw1);
+    if constexpr (RW2) load_tw_pass2<P>(q, tw, tw2);
     for (long long pr0 = (long long)blockIdx.x * G; pr0 < a.npairs; pr0 += (long long)gridDim.x * G) {
         const long long pr = pr0 + s;
         const bool ok = pr < a.npairs;
         const long long roff = 2 * pr * a.rs;
         // ---- inverse transforms: team t owns fields 2t and 2t+1
         if (ok) {
-#pragma unroll
+#pragma unroll 1
             for (int ff = 0; ff < 2; ++ff) {
                 const int f = 2 * t + ff;
-                const cplx* ra = a.f[f] + roff;
+                const cplx* ra = a.base + f * a.fstride + roff;
                 const cplx* rb = ra + a.rs;
-                fft_pass1<P, INV, 1>(q, sm + f * NP, tw, [&](int n) {
+                fft_pass1_rw<P, INV, 1>(q, sm + f * NP, tw1, [&](int n) {
                     const int k = (n <= N / 2) ? n : N - n;
                     if (k >= kzin) return mk(0.0, 0.0);
-                    return pack_hermitian<N>(n, ra[k], rb[k]);
+                    return pack_hermitian<N>(n, NSB_LDCG(ra + k), NSB_LDCG(rb + k));
                 });
             }
         }
         __syncthreads();
         if constexpr (P::PASSES == 3) {
             if (ok) {
-#pragma unroll
-                for (int ff = 0; ff < 2; ++ff)
-                    for (int b = q; b < P::NB2; b += TP) fft_pass2<P, INV, 1>(b, sm + (2 * t + ff) * NP, tw);
+#pragma unroll 1
+                for (int ff = 0; ff < 2; ++ff) {
+                    if constexpr (RW2) fft_pass2_rw<P, INV, 1>(q, sm + (2 * t + ff) * NP, tw2);
+                    else for (int b = q; b < P::NB2; b += TP) fft_pass2<P, INV, 1>(b, sm + (2 * t + ff) * NP, tw);
+                }
             }
             __syncthreads();
         }
         if (ok) {
-#pragma unroll
+#pragma unroll 1
             for (int ff = 0; ff < 2; ++ff) {
                 cplx v[P::RL];
                 cplx* buf = sm + (2 * t + ff) * NP;
@@ -279,18 +301,20 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
             const int i1 = (t + 1) % 3, i2 = (t + 2) % 3;
             const cplx* u1 = sm + i1 * NP + rowbase;
             const cplx* u2 = sm + i2 * NP + rowbase;
-            const cplx* w1 = sm + (3 + i1) * NP + rowbase;
-            const cplx* w2 = sm + (3 + i2) * NP + rowbase;
+            const cplx* v1 = sm + (3 + i1) * NP + rowbase;   // vorticity components
+            const cplx* v2 = sm + (3 + i2) * NP + rowbase;
 #pragma unroll
-            for (int j = 0; j < P::R1; ++j) c[j] = cross_comp(u1[j], w2[j], u2[j], w1[j]);
-            fft_pass1_regs<P, FWD>(q, c, tw);
+            for (int j = 0; j < P::R1; ++j) c[j] = cross_comp(u1[j], v2[j], u2[j], v1[j]);
+            fft_pass1_regs_rw<P, FWD>(c, tw1);
         }
         __syncthreads();
         if (ok) fft_pass1_scatter<P, 1>(q, sm + t * NP, c);
         __syncthreads();
         if constexpr (P::PASSES == 3) {
-            if (ok)
-                for (int b = q; b < P::NB2; b += TP) fft_pass2<P, FWD, 1>(b, sm + t * NP, tw);
+            if (ok) {
+                if constexpr (RW2) fft_pass2_rw<P, FWD, 1>(q, sm + t * NP, tw2);
+                else for (int b = q; b < P::NB2; b += TP) fft_pass2<P, FWD, 1>(b, sm + t * NP, tw);
+            }
             __syncthreads();
         }
         cplx v[P::RL];
@@ -302,7 +326,7 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
         }
         __syncthreads();
         if (ok) {
-            cplx* ra = a.f[t] + roff;
+            cplx* ra = a.base + t * a.fstride + roff;
             cplx* rb = ra + a.rs;
             const cplx* buf = sm + t * NP;
 #pragma unroll

@@ -238,7 +238,8 @@ static int run_pass_full(nsb200_ctx* h, char axis, int dir, int nfields, cplx* c
 static int run_z(nsb200_ctx* h, int which, int nfields, cplx* const* f, int rs, int kz_in, int kz_out) {
     ZArgs a;
     memset(&a, 0, sizeof a);
-    for (int i = 0; i < (which == NSB_Z_FUSED ? 6 : nfields); ++i) a.f[i] = f[i];
+    a.base = f[0];
+    a.fstride = (long long)h->field_elems;   // W[] and R[] are contiguous runs of fields
     a.tw = h->tw;
     a.rs = rs;
     a.npairs = (long long)h->N * h->ny_loc / 2;

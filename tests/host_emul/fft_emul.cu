@@ -109,10 +109,15 @@ template <class P> int check_fused() {
     // inverse
     for (int t = 0; t < 3; ++t) for (int ff = 0; ff < 2; ++ff) for (int q = 0; q < TP; ++q) {
         int f = 2 * t + ff;
-        fft_pass1<P, INV, 1>(q, sm.data() + f * NP, tw.data(), [&](int n) { int k = n <= N / 2 ? n : N - n; return pack_hermitian<N>(n, rows[f][0][k], rows[f][1][k]); });
+        cplx w1[P::R1 - 1]; load_tw_pass1<P>(q, tw.data(), w1);
+        fft_pass1_rw<P, INV, 1>(q, sm.data() + f * NP, w1, [&](int n) { int k = n <= N / 2 ? n : N - n; return pack_hermitian<N>(n, rows[f][0][k], rows[f][1][k]); });
     }
+    constexpr bool RW2 = (P::PASSES == 3) && (P::NB2 == TP);
     if constexpr (P::PASSES == 3)
-        for (int f = 0; f < 6; ++f) for (int b = 0; b < P::NB2; ++b) fft_pass2<P, INV, 1>(b, sm.data() + f * NP, tw.data());
+        for (int f = 0; f < 6; ++f) for (int b = 0; b < P::NB2; ++b) {
+            if constexpr (RW2) { cplx w2[P::R2 - 1]; load_tw_pass2<P>(b, tw.data(), w2); fft_pass2_rw<P, INV, 1>(b, sm.data() + f * NP, w2); }
+            else fft_pass2<P, INV, 1>(b, sm.data() + f * NP, tw.data());
+        }
     for (int f = 0; f < 6; ++f) for (int q = 0; q < TP; ++q) {
         cplx v[P::RL]; fft_pass_last<P, INV, 1>(q, sm.data() + f * NP, v);
         for (int j = 0; j < P::RL; ++j) sm[f * NP + rowbase(q) + j] = v[j];
@@ -140,12 +145,15 @@ template <class P> int check_fused() {
         cplx c[P::R1];
         for (int j = 0; j < P::R1; ++j)
             c[j] = cross_comp(sm[i1 * NP + rowbase(q) + j], sm[(3 + i2) * NP + rowbase(q) + j], sm[i2 * NP + rowbase(q) + j], sm[(3 + i1) * NP + rowbase(q) + j]);
-        fft_pass1_regs<P, FWD>(q, c, tw.data());
+        { cplx w1[P::R1 - 1]; load_tw_pass1<P>(q, tw.data(), w1); fft_pass1_regs_rw<P, FWD>(c, w1); }
         for (int j = 0; j < P::R1; ++j) creg[t * TP + q][j] = c[j];
     }
     for (int t = 0; t < 3; ++t) for (int q = 0; q < TP; ++q) fft_pass1_scatter<P, 1>(q, sm.data() + t * NP, creg[t * TP + q].data());
     if constexpr (P::PASSES == 3)
-        for (int t = 0; t < 3; ++t) for (int b = 0; b < P::NB2; ++b) fft_pass2<P, FWD, 1>(b, sm.data() + t * NP, tw.data());
+        for (int t = 0; t < 3; ++t) for (int b = 0; b < P::NB2; ++b) {
+            if constexpr (RW2) { cplx w2[P::R2 - 1]; load_tw_pass2<P>(b, tw.data(), w2); fft_pass2_rw<P, FWD, 1>(b, sm.data() + t * NP, w2); }
+            else fft_pass2<P, FWD, 1>(b, sm.data() + t * NP, tw.data());
+        }
     std::vector<std::vector<cplx>> vreg(3 * TP, std::vector<cplx>(P::RL));
     for (int t = 0; t < 3; ++t) for (int q = 0; q < TP; ++q) {
         cplx v[P::RL]; fft_pass_last<P, FWD, 1>(q, sm.data() + t * NP, v);
