@@ -17,6 +17,7 @@ SYMBOLS = [
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     ("nsb200_destroy", ctypes.c_int, [ctypes.c_void_p]),
     ("nsb200_get_nccl_unique_id", ctypes.c_int, [ctypes.c_void_p]),
+    ("nsb200_exchange_layout", ctypes.c_int, [ctypes.c_long, ctypes.c_int, ctypes.c_long, _LP]),
     ("nsb200_local_slab", ctypes.c_int, [ctypes.c_void_p, _LP, _LP]),
     ("nsb200_local_fourier_elems", ctypes.c_long, [ctypes.c_void_p]),
     ("nsb200_upload_uhat", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -36,6 +37,7 @@ SYMBOLS = [
     ("nsb200_time_op", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, _DP]),
     ("nsb200_profile", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     ("nsb200_profile_read", ctypes.c_int, [ctypes.c_void_p, _DP, _LP]),
+    ("nsb200_profile_bytes", ctypes.c_int, [ctypes.c_void_p, _DP]),
     ("nsb200_launch_count", ctypes.c_long, [ctypes.c_void_p]),
     ("nsb200_device_bytes", ctypes.c_long, [ctypes.c_void_p]),
 ]

@@ -141,6 +141,7 @@ struct nsb200_ctx {
     size_t bytes = 0;
     bool prof_on = false;
     struct ProfRec { int cls; cudaEvent_t a, b; };
+    double prof_bytes[NSB200_PC_COUNT] = {0};   // algorithmic (minimal) bytes of the launches recorded, per class
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
     Geom geom(bool windowed = false) const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.x_start = x_start; g.kcut = windowed ? kmax : N; return g; }
@@ -161,8 +162,8 @@ static cudaEvent_t prof_event(nsb200_ctx* h) {
 }
 struct ProfScope {
     nsb200_ctx* h; cudaEvent_t a = nullptr, b = nullptr; int cls;
-    ProfScope(nsb200_ctx* h_, int cls_) : h(h_), cls(cls_) {
-        if (h->prof_on) { a = prof_event(h); b = prof_event(h); cudaEventRecord(a, h->stream); }
+    ProfScope(nsb200_ctx* h_, int cls_, double algo_bytes = 0.0) : h(h_), cls(cls_) {
+        if (h->prof_on) { a = prof_event(h); b = prof_event(h); cudaEventRecord(a, h->stream); h->prof_bytes[cls] += algo_bytes; }
     }
     ~ProfScope() {
         if (a) { cudaEventRecord(b, h->stream); h->prof.push_back({cls, a, b}); }
@@ -178,6 +179,17 @@ struct ProfScope {
 // transformed-axis wavenumbers |k| > kmax (not loaded); `out_w` = outputs with |k| > kmax are not stored
 // (the dealias mask zeroes them); `outer_w` = pencils whose outer wavenumber is > kmax are skipped;
 // nzv = number of kz columns carried.
+// Block layout of the slab all-to-all (pure host logic, exported as nsb200_exchange_layout so the CPU
+// tests can drive it): element (i_local, n, kz) of a y pencil, n being the y index, lives at
+//   (n >> shift) * block + i_local * outer + (n & mask) * rs + kz
+// so that everything destined to rank (n >> shift) is one contiguous block of `block` elements.
+static void exchange_layout(long N, int n_ranks, long rs, long out[5]) {
+    const long ny_loc = N / n_ranks, nx_loc = N / n_ranks;
+    long sh = 0;
+    while ((1L << sh) < ny_loc) ++sh;
+    out[0] = sh; out[1] = ny_loc - 1; out[2] = nx_loc * ny_loc * rs; out[3] = ny_loc * rs; out[4] = rs;
+}
+
 struct PassSpec {
     char axis; int dir; char exch;
     int in_rs, out_rs;       // row strides (complex elements) of source / destination
@@ -207,14 +219,13 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         a.in_so = (long long)N * ps.in_rs;  a.in_s2 = ps.in_rs;
         a.out_so = (long long)N * ps.out_rs; a.out_s2 = ps.out_rs;
         if (h->nranks > 1 && ps.exch != 'n') {
-            int sh = 0;
-            while ((1 << sh) < h->ny_loc) ++sh;
+            long L[5];
             if (ps.exch == 'o') {
-                a.out_shift = sh; a.out_mask = h->ny_loc - 1;
-                a.out_s1 = (long long)h->nx_loc * h->ny_loc * ps.out_rs; a.out_so = (long long)h->ny_loc * ps.out_rs;
+                exchange_layout(N, h->nranks, ps.out_rs, L);
+                a.out_shift = (int)L[0]; a.out_mask = (int)L[1]; a.out_s1 = L[2]; a.out_so = L[3];
             } else {
-                a.in_shift = sh; a.in_mask = h->ny_loc - 1;
-                a.in_s1 = (long long)h->nx_loc * h->ny_loc * ps.in_rs; a.in_so = (long long)h->ny_loc * ps.in_rs;
+                exchange_layout(N, h->nranks, ps.in_rs, L);
+                a.in_shift = (int)L[0]; a.in_mask = (int)L[1]; a.in_s1 = L[2]; a.in_so = L[3];
             }
         }
     } else {
@@ -223,7 +234,10 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         a.out_so = ps.out_rs; a.out_s2 = (long long)h->ny_loc * ps.out_rs;
     }
     {
-        ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD));
+        // minimal traffic: every carried pencil reads its non-zero inputs and writes its kept outputs once
+        const double in_cnt = ps.in_w ? 2 * K + 1 : N, out_cnt = ps.out_w ? 2 * K + 1 : N;
+        const double bytes = 16.0 * field_cnt * (double)n_outer * ps.nzv * (in_cnt + out_cnt);
+        ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD), bytes);
         CKI(h->ops->strided(ps.dir, &a, n_outer, field_cnt, h->stream));
     }
     h->launches++;
@@ -249,7 +263,11 @@ static int run_z(nsb200_ctx* h, int which, int nfields, cplx* const* f, int rs, 
     long long want = (a.npairs + gpc - 1) / gpc;
     int grid = (int)(want < h->zgrid[which] ? want : h->zgrid[which]);
     {
-        ProfScope ps(h, which == NSB_Z_FUSED ? NSB200_PC_Z_FUSED : which == NSB_Z_C2R ? NSB200_PC_Z_C2R : NSB200_PC_Z_R2C);
+        const double rows = 2.0 * (double)a.npairs;
+        const double bytes = which == NSB_Z_FUSED ? rows * 16.0 * (6.0 * kz_in + 3.0 * kz_out)
+                           : which == NSB_Z_C2R ? nfields * rows * (16.0 * kz_in + 8.0 * h->N)
+                                                : nfields * rows * (8.0 * h->N + 16.0 * kz_out);
+        ProfScope ps(h, which == NSB_Z_FUSED ? NSB200_PC_Z_FUSED : which == NSB_Z_C2R ? NSB200_PC_Z_C2R : NSB200_PC_Z_R2C, bytes);
         CKI(h->ops->z(which, &a, nfields, grid, h->stream));
     }
     h->launches++;
@@ -288,7 +306,8 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs) {
     ca.g = h->geom(in_w);
     ca.w_rs = rs;
     {
-        ProfScope ps(h, NSB200_PC_CURL);
+        const double kw = in_w ? 2.0 * h->kmax + 1 : h->N;   // kx planes are counted globally / nranks (slab average)
+        ProfScope ps(h, NSB200_PC_CURL, 16.0 * 6.0 * (kw * kw / h->nranks) * nz_in);
         k_curl<<<rg, 128, 0, h->stream>>>(ca);
     }
     CK(cudaGetLastError());
@@ -353,7 +372,11 @@ static int rk_stage(nsb200_ctx* h, int stage, double dt, int c_rs, bool in_w) {
     const double n3 = (double)h->N * (double)h->N * (double)h->N;
     a.norm = 1.0 / (n3 * n3);   // 1/pow(Nx*Ny*Nz, 2.0), solver.c:631 (exact for powers of two)
     {
-        ProfScope ps(h, NSB200_PC_RK);
+        const double kw = a.skip_outside ? 2.0 * h->kmax + 1 : h->N;
+        const double nk = a.skip_outside ? h->kmax + 1 : h->nzf;
+        const double nc = out_w ? (2.0 * h->kmax + 1) * (2.0 * h->kmax + 1) * (h->kmax + 1) / h->nranks : (double)h->nrows() * h->nzf;
+        const double arrays = stage == 0 ? 9.0 : stage == 3 ? 9.0 : stage == 4 ? 3.0 : 12.0;   // besides c: u, acc, tmp reads/writes
+        ProfScope ps(h, NSB200_PC_RK, 16.0 * (3.0 * nc + arrays * (kw * kw / h->nranks) * nk));
         k_rk_stage<<<h->row_grid(), 128, 0, h->stream>>>(a);
     }
     CK(cudaGetLastError());
@@ -412,6 +435,12 @@ extern "C" {
 
 const char* nsb200_version(void) { return "nsb200 0.1 sm_100a"; }
 const char* nsb200_last_error(void) { return g_err.c_str(); }
+
+int nsb200_exchange_layout(long N, int n_ranks, long row_stride, long out[5]) {
+    if (!out || n_ranks < 1 || N < 1 || N % n_ranks != 0) return fail("nsb200_exchange_layout: bad argument");
+    exchange_layout(N, n_ranks, row_stride, out);
+    return 0;
+}
 
 int nsb200_get_nccl_unique_id(void* out128) {
     CKR(load_nccl());
@@ -792,6 +821,11 @@ int nsb200_spectra(nsb200_ctx* h, double* enrg_spect, double* enst_spect, int n_
 int nsb200_profile(nsb200_ctx* h, int enable) {
     if (!h) return fail("nsb200_profile: null handle");
     h->prof_on = enable != 0;
+    return 0;
+}
+int nsb200_profile_bytes(nsb200_ctx* h, double bytes[NSB200_PC_COUNT]) {
+    if (!h || !bytes) return fail("nsb200_profile_bytes: null argument");
+    for (int i = 0; i < NSB200_PC_COUNT; ++i) { bytes[i] = h->prof_bytes[i]; h->prof_bytes[i] = 0.0; }
     return 0;
 }
 int nsb200_profile_read(nsb200_ctx* h, double ms[NSB200_PC_COUNT], long counts[NSB200_PC_COUNT]) {

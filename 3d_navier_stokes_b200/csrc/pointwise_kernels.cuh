@@ -410,7 +410,7 @@ __global__ void k_ic_real(const IcArgs a) {
 
 // Partition independent random-phase solenoidal field: each mode depends only
 // on (seed, kx, ky, kz); Hermitian on the kz = 0 plane by construction.  Bit-identical integer
-// hashing to oracle/ns_oracle.py::_mode_uniform.
+// hashing to the test-side generator (DESIGN.md "synthetic inputs").
 NSB_HD unsigned long long nsb_splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
     unsigned long long z = x;

@@ -164,11 +164,13 @@ class Solver:
         self.lib.check(self.lib.nsb200_profile(self.h, 1 if enable else 0), "nsb200_profile")
 
     def profile_read(self):
-        """{class name: (summed ms, launches)} since the last read."""
+        """{class name: (summed ms, launches, algorithmic bytes)} since the last read."""
         ms = (ctypes.c_double * capi.PC_COUNT)()
         cnt = (ctypes.c_long * capi.PC_COUNT)()
         self.lib.check(self.lib.nsb200_profile_read(self.h, ms, cnt), "nsb200_profile_read")
-        return {name: (ms[i], cnt[i]) for i, name in enumerate(capi.PC_NAMES) if cnt[i]}
+        by = (ctypes.c_double * capi.PC_COUNT)()
+        self.lib.check(self.lib.nsb200_profile_bytes(self.h, by), "nsb200_profile_bytes")
+        return {name: (ms[i], cnt[i], by[i]) for i, name in enumerate(capi.PC_NAMES) if cnt[i]}
 
     def launch_count(self):
         return int(self.lib.nsb200_launch_count(self.h))

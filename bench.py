@@ -196,9 +196,6 @@ def reference_arm(n, steps, warmup, budget_s, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-# algorithmic bytes per launch in units of S = bytes of one scalar field (DESIGN.md "kernels")
-ALGO_S = {"curl": 6.0, "y_inv": 12.0, "x_inv": 12.0, "z_fused": 9.0, "x_fwd": 6.0, "y_fwd": 6.0, "rk": 13.5}
-
 
 def ours(args):
     import numpy as np
@@ -295,9 +292,9 @@ def ours(args):
         peak, peak_src = peaks()
         tot_prof = sum(v[0] for v in prof.values()) or 1.0
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else "z_fused"
-        dom_ms, dom_cnt = prof.get(dom, (0.0, 0))
+        dom_ms, dom_cnt, dom_bytes = prof.get(dom, (0.0, 0, 0.0))
         per_launch_ms = dom_ms / max(dom_cnt, 1)
-        algo_bytes = ALGO_S[dom] * S / world
+        algo_bytes = dom_bytes / max(dom_cnt, 1)   # minimal bytes per launch as the library accounts them
         achieved = algo_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         traffic = None
         try:
@@ -315,6 +312,9 @@ def ours(args):
                          "share_of_step": dom_ms / tot_prof,
                          "step_frac_204S": 204.0 * S / world / (ms_per_step * 1e-3) / 1e9 / peak},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "kernel_hbm_frac": {k: (v[2] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else None) for k, v in prof.items()},
+            "step_algorithmic_bytes": sum(v[2] for v in prof.values()) / args.steps,
+            "step_hbm_frac": sum(v[2] for v in prof.values()) / args.steps / (ms_per_step * 1e-3) / 1e9 / peak,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": slab_bytes * world / args.steps,
                     "d2h_bytes_per_step": slab_bytes * world / args.steps + 160.0 * world,
                     "what": "one save interval through the C ABI with pinned host buffers: upload u_hat, %d x (RK4Step + "

@@ -61,6 +61,13 @@ int nsb200_destroy(nsb200_ctx* h);
  * torch.distributed). */
 int nsb200_get_nccl_unique_id(void* out128);
 
+/* Layout of the slab exchange buffers (pure host logic, no device needed): element (i_local, y, kz) of the
+ * y-transformed Fourier slab is stored at  (y >> out[0]) * out[2] + i_local * out[3] + (y & out[1]) * out[4] + kz,
+ * i.e. one contiguous block of out[2] complex elements per destination rank; after the all-to-all the blocks
+ * received from ranks 0..P-1, in order, form [kx][y_local][kz].  Replaces the transposes FFTW-MPI does inside
+ * fftw_mpi_execute_dft_* (solver.c:656-683). */
+int nsb200_exchange_layout(long N, int n_ranks, long row_stride, long out[5]);
+
 /* sys_vars->local_Nx / local_Nx_start as fftw_mpi_local_size_many reports them (solver.c:1845). */
 int nsb200_local_slab(nsb200_ctx* h, long* local_nx, long* local_nx_start);
 /* Number of double _Complex elements of a local Fourier vector field (= alloc_local_batch). */
@@ -147,6 +154,9 @@ int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_
 #define NSB200_PC_COUNT 16
 int nsb200_profile(nsb200_ctx* h, int enable);
 int nsb200_profile_read(nsb200_ctx* h, double ms[NSB200_PC_COUNT], long counts[NSB200_PC_COUNT]);
+/* Algorithmic (minimal) HBM bytes of the launches recorded since the last call, per class: every carried
+ * element read once and written once, with the dealias-support pruning in effect. */
+int nsb200_profile_bytes(nsb200_ctx* h, double bytes[NSB200_PC_COUNT]);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 long nsb200_launch_count(nsb200_ctx* h);
 /* Bytes of device memory held by the handle. */

@@ -41,4 +41,23 @@ void FinalWriteAndCloseOutputFile(const long int* N, int iters, int save_data_in
 	nsb_ref_final_uhat = (double*)malloc(sizeof(double) * (size_t)n);
 	nsb_ref_final_uhat_len = n;
 	memcpy(nsb_ref_final_uhat, run_data->u_hat, sizeof(double) * (size_t)n);
+	/* stand-alone executables (host/_build/solver_*): NSB_IO_STUB_DIR=<dir> dumps the series and final state */
+	const char* dir = getenv("NSB_IO_STUB_DIR");
+	if (dir && !sys_vars->rank) {
+		char path[1024];
+		snprintf(path, sizeof path, "%s/series.txt", dir);
+		FILE* f = fopen(path, "w");
+		if (f) {
+			for (long s = 0; s < rows; ++s)
+				fprintf(f, "%.17g %.17g %.17g %.17g %.17g %.17g\n", nsb_ref_series[6 * s], nsb_ref_series[6 * s + 1], nsb_ref_series[6 * s + 2],
+				        nsb_ref_series[6 * s + 3], nsb_ref_series[6 * s + 4], nsb_ref_series[6 * s + 5]);
+			fclose(f);
+		}
+		snprintf(path, sizeof path, "%s/u_hat_final.bin", dir);
+		f = fopen(path, "wb");
+		if (f) { fwrite(nsb_ref_final_uhat, sizeof(double), (size_t)n, f); fclose(f); }
+		snprintf(path, sizeof path, "%s/n_writes.txt", dir);
+		f = fopen(path, "w");
+		if (f) { fprintf(f, "%ld\n", nsb_ref_n_writes); fclose(f); }
+	}
 }

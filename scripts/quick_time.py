@@ -43,4 +43,10 @@ for n in sizes:
         moved = 4 * 66 * S
         print("  %-20s %9.4f ms  %6.2f steps/s  204S model %5.1f%%, moved(264S) %5.1f%% of peak" %
               ("RK4 step", ms, 1e3 / ms, 100 * 204 * S / ms / 1e6 / peak, 100 * moved / ms / 1e6 / peak))
+        s.profile(True)
+        s.time_op(capi.OP_RK4_STEP, 4, dt)
+        pr = s.profile_read()
+        s.profile(False)
+        tot = sum(v[0] for v in pr.values())
+        print("  per step: " + "  ".join("%s %.2f ms %.0f%%" % (k, v[0] / 4, 100 * v[2] / (v[0] * 1e-3) / 1e9 / peak) for k, v in pr.items()) + "  | sum %.2f ms, %.1f GB/step algorithmic" % (tot / 4, sum(v[2] for v in pr.values()) / 4e9))
         print("  E after run: %.12g" % s.compute_system_measurables()[0])

@@ -1,0 +1,76 @@
+"""World-size-2 (and 4) gloo test of the N > 1 host logic, on CPU: the kx-slab partition and the block layout
+of the slab all-to-all that sits between the y pass and the x pass of every 3-D transform
+(nsb200_exchange_layout, the function run_pass() uses to place the y-pass output).  Each rank transforms its
+slab along y with NumPy, places the result with the library's layout, exchanges the blocks with
+torch.distributed all_to_all_single, transforms along x, and must reproduce the 2-D transform of the global
+field on its y slab - the same data flow the GPU kernels follow."""
+import ctypes
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+capi = importlib.import_module("3d_navier_stokes_b200.capi")
+pytestmark = pytest.mark.skipif(not os.path.exists(capi.lib_path()), reason="libnsb200.so not built")
+
+
+def _worker(rank, world, n, rs, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = capi.load()
+        L = (ctypes.c_long * 5)()
+        assert lib.nsb200_exchange_layout(n, world, rs, L) == 0
+        shift, mask, block, outer, row = [int(v) for v in L]
+        nzf = n // 2 + 1
+        nx_loc = ny_loc = n // world
+        rng = np.random.default_rng(1234)                      # same global field on every rank
+        glob = rng.standard_normal((n, n, nzf)) + 1j * rng.standard_normal((n, n, nzf))
+        mine = glob[rank * nx_loc:(rank + 1) * nx_loc]        # Fourier slab [kx_loc][ky][kz]
+        ypass = np.fft.ifft(mine, axis=1) * n                  # unnormalised inverse along y
+        send = np.zeros(world * block, dtype=np.complex128)
+        i, y, k = np.meshgrid(np.arange(nx_loc), np.arange(n), np.arange(nzf), indexing="ij")
+        send[(y >> shift) * block + i * outer + (y & mask) * row + k] = ypass
+        recv = np.empty_like(send)
+        ts, tr = torch.from_numpy(send.view(np.float64)), torch.from_numpy(recv.view(np.float64))
+        dist.all_to_all_single(tr, ts)
+        got = recv.reshape(n, ny_loc, rs)[:, :, :nzf]         # [kx][y_loc][kz]
+        xpass = np.fft.ifft(got, axis=0) * n
+        ref = np.fft.ifft2(glob, axes=(0, 1)) * n * n
+        err = np.abs(xpass - ref[:, rank * ny_loc:(rank + 1) * ny_loc, :]).max() / np.abs(ref).max()
+        # reverse direction: forward x pass, exchange back, forward y pass with the layout on the INPUT side
+        fx = np.fft.fft(xpass, axis=0)                         # [kx][y_loc][kz]
+        back_send = np.zeros(world * block, dtype=np.complex128)
+        back_send.reshape(n, ny_loc, rs)[:, :, :nzf] = fx      # block r = kx planes of rank r: already contiguous
+        back_recv = np.empty_like(back_send)
+        dist.all_to_all_single(torch.from_numpy(back_recv.view(np.float64)), torch.from_numpy(back_send.view(np.float64)))
+        gathered = back_recv[(y >> shift) * block + i * outer + (y & mask) * row + k]   # [kx_loc][y][kz]
+        fy = np.fft.fft(gathered, axis=1)
+        err2 = np.abs(fy / (n * n) - mine).max() / np.abs(mine).max()
+        q.put((rank, float(err), float(err2)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,rs", [(2, 16, 16), (2, 32, 24), (4, 16, 9)])
+def test_slab_exchange_layout_over_gloo(world, n, rs):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + world * 10 + n % 7
+    procs = [ctx.Process(target=_worker, args=(r, world, n, rs, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == list(range(world))
+    for _, e1, e2 in res:
+        assert e1 < 1e-13 and e2 < 1e-13
