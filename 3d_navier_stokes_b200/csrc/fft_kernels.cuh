@@ -33,6 +33,7 @@
 #endif
 
 #define NSB_MAX_FIELDS 6
+#define NSB_MAX_PEERS 8
 
 // ------------------------------------------------------------------------------ strided c2c pass
 struct StridedArgs {
@@ -53,12 +54,20 @@ struct StridedArgs {
     int in_zero_hi;
     int out_skip_lo;    // transformed-axis outputs in [out_skip_lo, out_skip_hi) are not stored
     int out_skip_hi;
+    // Fused slab exchange: when out_p2p != 0 the output block of destination rank r = n >> out_shift is stored
+    // straight into rank r's receive buffer over NVLink: peer_delta[r] is the byte distance from this rank's
+    // slab allocation to rank r's (CUDA IPC mapping; 0 for r == self), out_s1 is not used and dst[] already
+    // includes this rank's block offset inside the receiver's buffer.
+    int out_p2p;
+    long long peer_delta[NSB_MAX_PEERS];
 };
 
 template <class P, int T, int TP, int DIR>
 __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a) {
     extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
     cplx* smem = reinterpret_cast<cplx*>(nsb_smem_raw);
+    __shared__ long long s_delta[NSB_MAX_PEERS];
+    if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = a.peer_delta[threadIdx.x];   // read after the pass barriers
     const int p = threadIdx.x % T;
     const int q = threadIdx.x / T;
     const int field = blockIdx.z;
@@ -85,6 +94,24 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a) {
         __syncthreads();
     }
     const int slo = a.out_skip_lo, shi = a.out_skip_hi;
+    if (a.out_p2p) {
+        // store phase doubles as the slab all-to-all: each destination rank's block goes to that rank's memory
+        for (int b = q; b < P::NBL; b += TP) {
+            cplx v[P::RL];
+            fft_pass_last<P, DIR, T>(b, sm, v);
+            if (valid) {
+#pragma unroll
+                for (int k2 = 0; k2 < P::RL; ++k2) {
+                    const int n = b + k2 * P::NBL;
+                    if (!(n >= slo && n < shi)) {
+                        cplx* d = reinterpret_cast<cplx*>(reinterpret_cast<char*>(dst) + s_delta[n >> osh]);
+                        d[(long long)(n & omk) * os2] = v[k2];
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (int b = q; b < P::NBL; b += TP) {
         cplx v[P::RL];
         fft_pass_last<P, DIR, T>(b, sm, v);

@@ -53,6 +53,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -76,6 +77,7 @@ static int load_nccl() {
     NSB_SYM(Send, "ncclSend")
     NSB_SYM(Recv, "ncclRecv")
     NSB_SYM(AllReduce, "ncclAllReduce")
+    NSB_SYM(AllGather, "ncclAllGather")
     NSB_SYM(GroupStart, "ncclGroupStart")
     NSB_SYM(GroupEnd, "ncclGroupEnd")
     NSB_SYM(GetErrorString, "ncclGetErrorString")
@@ -135,6 +137,10 @@ struct nsb200_ctx {
     std::vector<cudaEvent_t> ev_comm;
     const FftOps* ops = nullptr;
     ncclComm_t comm = nullptr;
+    void* peer_slab[NSB_MAX_PEERS] = {nullptr};   // CUDA IPC mappings of every rank's slab allocation (self = own pointer)
+    long long peer_delta[NSB_MAX_PEERS] = {0};
+    bool p2p = false;                              // slab exchange fused into the FFT store phase over NVLink
+    int* bar_dev = nullptr;
     int sm_count = 0;
     int zgrid[3] = {0, 0, 0};
     long launches = 0;
@@ -195,6 +201,7 @@ struct PassSpec {
     int in_rs, out_rs;       // row strides (complex elements) of source / destination
     int nzv;
     bool in_w, out_w, outer_w;
+    bool p2p_out = false;    // store each destination rank's block into that rank's buffer (peer memory)
 };
 static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* const* dst, int field0, int field_cnt) {
     StridedArgs a;
@@ -223,6 +230,11 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
             if (ps.exch == 'o') {
                 exchange_layout(N, h->nranks, ps.out_rs, L);
                 a.out_shift = (int)L[0]; a.out_mask = (int)L[1]; a.out_s1 = L[2]; a.out_so = L[3];
+                if (ps.p2p_out) {   // receiver-side layout [source rank][kx_loc][y_loc][rs]: this rank's block
+                    a.out_p2p = 1; a.out_s1 = 0;
+                    for (int f = 0; f < field_cnt; ++f) a.dst[f] += (long long)h->rank * L[2];
+                    for (int r = 0; r < h->nranks; ++r) a.peer_delta[r] = h->peer_delta[r];
+                }
             } else {
                 exchange_layout(N, h->nranks, ps.in_rs, L);
                 a.in_shift = (int)L[0]; a.in_mask = (int)L[1]; a.in_s1 = L[2]; a.in_so = L[3];
@@ -232,6 +244,15 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         n_outer = h->ny_loc;
         a.in_so = ps.in_rs;  a.in_s2 = (long long)h->ny_loc * ps.in_rs;
         a.out_so = ps.out_rs; a.out_s2 = (long long)h->ny_loc * ps.out_rs;
+        if (ps.p2p_out) {
+            // forward x pass: output plane kx belongs to rank kx / nx_loc; it lands in that rank's buffer at
+            // [this rank (y-slab owner)][kx_loc][y_loc][rs], the input layout of the forward y pass
+            long L[5];
+            exchange_layout(N, h->nranks, ps.out_rs, L);
+            a.out_p2p = 1; a.out_shift = (int)L[0]; a.out_mask = (int)L[1]; a.out_s1 = 0;
+            for (int f = 0; f < field_cnt; ++f) a.dst[f] += (long long)h->rank * L[2];
+            for (int r = 0; r < h->nranks; ++r) a.peer_delta[r] = h->peer_delta[r];
+        }
     }
     {
         // minimal traffic: every carried pencil reads its non-zero inputs and writes its kept outputs once
@@ -287,12 +308,19 @@ static int exchange(nsb200_ctx* h, cplx* const* send, cplx* const* recv, int fie
     return 0;
 }
 
+// Cross-GPU barrier on the compute stream: every rank's preceding kernels (and their stores into peer memory)
+// are complete before any rank's following kernels start.
+static int gpu_barrier(nsb200_ctx* h) {
+    CKN(g_nccl.AllReduce(h->bar_dev, h->bar_dev, 1, ncclInt32, ncclSum, h->comm, h->stream));
+    return 0;
+}
+
 // NonlinearRHSBatch up to (not including) normalise/project/dealias: raw (u x w)^ of `in` left in R[0..2]
 // (row stride returned in *c_rs).  solver.c:637-683.  in_w: `in` is known to vanish outside the dealias
 // cube, so the inverse transforms skip those modes.  The forward transforms skip the modes the dealias
 // mask will zero whenever dealiasing is on.  Multi-rank: per-field pipelining of y pass -> all-to-all ->
 // x pass over two streams.
-static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs) {
+static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx*** c_out) {
     const bool out_w = h->prune && h->dealias == NSB200_DEALIAS_23;
     in_w = in_w && h->prune;
     // workspace row stride: compact when both directions carry kz <= kmax only
@@ -300,9 +328,12 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs) {
     const int nz_in = in_w ? h->kmax + 1 : h->nzf;
     const int nz_out = out_w ? h->kmax + 1 : h->nzf;
     *c_rs = rs;
+    *c_out = h->p2p ? h->W : h->R;   // where the raw (u x w)^ ends up
     const int rg = h->row_grid();
     CurlArgs ca;
-    for (int d = 0; d < 3; ++d) { ca.u[d] = in[d]; ca.w[d] = h->R[3 + d]; }
+    // curl output: R[3..5] feeds the y pass (NCCL path and single GPU, where R aliases W); with the fused
+    // exchange R is the receive side, so the curl goes to W[0..2]
+    for (int d = 0; d < 3; ++d) { ca.u[d] = in[d]; ca.w[d] = h->p2p ? h->W[d] : h->R[3 + d]; }
     ca.g = h->geom(in_w);
     ca.w_rs = rs;
     {
@@ -328,6 +359,23 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs) {
         CKR(run_pass(h, xfwd, h->W, h->W, 0, 3));
         CKR(run_pass(h, yfwd, h->W, h->R, 0, 3));   // R aliases W when nranks == 1
         return 0;
+    }
+    if (h->p2p) {
+        // Fused exchange: C = W[0..2] (curl output / forward result), Y = W[3..5] (forward receive), X = R (inverse
+        // receive).  The y pass stores into the peers' X, the forward x pass into the peers' Y; two barriers per
+        // stage order producers and consumers (DESIGN.md section 6 lists the hazards).
+        cplx* srcp[6] = {in[0], in[1], in[2], h->W[0], h->W[1], h->W[2]};
+        yinv_u.p2p_out = yinv_w.p2p_out = true;
+        xfwd.p2p_out = true;
+        CKR(run_pass(h, yinv_u, srcp, h->R, 0, 3));
+        CKR(run_pass(h, yinv_w, srcp, h->R, 3, 3));
+        CKR(gpu_barrier(h));
+        CKR(run_pass(h, xinv, h->R, h->R, 0, 6));
+        CKR(run_z(h, NSB_Z_FUSED, 3, h->R, rs, nz_in, nz_out));
+        CKR(run_pass(h, xfwd, h->R, h->W + 3, 0, 3));
+        CKR(gpu_barrier(h));
+        CKR(run_pass(h, yfwd, h->W + 3, h->W, 0, 3));
+        return 0;   // result in W[0..2]
     }
     // inverse: y pass (field f) | exchange (field f) | x pass (field f), pipelined across fields
     for (int f = 0; f < 6; ++f) {
@@ -355,10 +403,10 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs) {
     return 0;
 }
 
-static int rk_stage(nsb200_ctx* h, int stage, double dt, int c_rs, bool in_w) {
+static int rk_stage(nsb200_ctx* h, int stage, double dt, int c_rs, bool in_w, cplx* const* c) {
     RkArgs a;
     memset(&a, 0, sizeof a);
-    for (int d = 0; d < 3; ++d) { a.c[d] = h->R[d]; a.u[d] = h->U[d]; a.tmp[d] = h->TMP[d]; a.acc[d] = h->ACC[d]; a.uout[d] = h->U[d]; }
+    for (int d = 0; d < 3; ++d) { a.c[d] = c[d]; a.u[d] = h->U[d]; a.tmp[d] = h->TMP[d]; a.acc[d] = h->ACC[d]; a.uout[d] = h->U[d]; }
     const bool out_w = h->prune && h->dealias == NSB200_DEALIAS_23;
     a.g = h->geom(out_w);
     a.c_rs = c_rs;
@@ -388,10 +436,11 @@ static int step(nsb200_ctx* h, double dt) {
     // U (and hence every stage input U + a dt k_i) stays inside the dealias cube once it is there
     const bool w = h->u_in_window && h->dealias == NSB200_DEALIAS_23;
     int crs = 0;
-    CKR(rhs_raw(h, h->U, w, &crs));   CKR(rk_stage(h, 0, dt, crs, w));   // solver.c:522-536
-    CKR(rhs_raw(h, h->TMP, w, &crs)); CKR(rk_stage(h, 1, dt, crs, w));   // :538-552
-    CKR(rhs_raw(h, h->TMP, w, &crs)); CKR(rk_stage(h, 2, dt, crs, w));   // :554-568
-    CKR(rhs_raw(h, h->TMP, w, &crs)); CKR(rk_stage(h, 3, dt, crs, w));   // :570-607
+    cplx** c = nullptr;
+    CKR(rhs_raw(h, h->U, w, &crs, &c));   CKR(rk_stage(h, 0, dt, crs, w, c));   // solver.c:522-536
+    CKR(rhs_raw(h, h->TMP, w, &crs, &c)); CKR(rk_stage(h, 1, dt, crs, w, c));   // :538-552
+    CKR(rhs_raw(h, h->TMP, w, &crs, &c)); CKR(rk_stage(h, 2, dt, crs, w, c));   // :554-568
+    CKR(rhs_raw(h, h->TMP, w, &crs, &c)); CKR(rk_stage(h, 3, dt, crs, w, c));   // :570-607
     return 0;
 }
 
@@ -455,7 +504,10 @@ int nsb200_destroy(nsb200_ctx* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    for (int p = 0; p < NSB_MAX_PEERS; ++p)
+        if (h->peer_slab[p] && h->peer_slab[p] != (void*)h->slab) cudaIpcCloseMemHandle(h->peer_slab[p]);
     if (h->comm) g_nccl.CommDestroy(h->comm);
+    cudaFree(h->bar_dev);
     cudaFree(h->slab); cudaFree(h->tw); cudaFree(h->meas_partial); cudaFree(h->meas_dev); cudaFree(h->spect_dev); cudaFree(h->flag_dev);
     cudaFree(h->flush_buf);
     if (h->meas_host) cudaFreeHost(h->meas_host);
@@ -568,6 +620,42 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
         memcpy(&id, nccl_unique_id, sizeof id);
         ncclResult_t r = g_nccl.CommInitRank(&h->comm, n_ranks, id, rank);
         if (r != ncclSuccess) { fail(std::string("ncclCommInitRank failed: ") + g_nccl.GetErrorString(r)); nsb200_destroy(h); return 1; }
+        CKC(cudaMalloc(&h->bar_dev, 256));
+        CKC(cudaMemsetAsync(h->bar_dev, 0, 256, h->stream));
+        // Map every rank's slab allocation (CUDA IPC over NVLink) so the FFT store phases can write the
+        // slab exchange straight into the peers' receive buffers.  NSB200_NO_P2P=1 keeps the NCCL exchange.
+        const char* nop = getenv("NSB200_NO_P2P");
+        if (!(nop && nop[0] == '1') && n_ranks <= NSB_MAX_PEERS) {
+            cudaIpcMemHandle_t mine;
+            CKC(cudaIpcGetMemHandle(&mine, h->slab));
+            unsigned char* hd = nullptr;
+            CKC(cudaMalloc(&hd, sizeof(cudaIpcMemHandle_t) * (n_ranks + 1)));
+            CKC(cudaMemcpyAsync(hd + sizeof(mine) * n_ranks, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+            ncclResult_t r2 = g_nccl.AllGather(hd + sizeof(mine) * n_ranks, hd, sizeof mine, ncclUint8, h->comm, h->stream);
+            if (r2 != ncclSuccess) { fail(std::string("ncclAllGather failed: ") + g_nccl.GetErrorString(r2)); cudaFree(hd); nsb200_destroy(h); return 1; }
+            std::vector<cudaIpcMemHandle_t> all(n_ranks);
+            CKC(cudaMemcpyAsync(all.data(), hd, sizeof(mine) * n_ranks, cudaMemcpyDeviceToHost, h->stream));
+            CKC(cudaStreamSynchronize(h->stream));
+            cudaFree(hd);
+            bool okp = true;
+            for (int p = 0; p < n_ranks && okp; ++p) {
+                if (p == rank) { h->peer_slab[p] = h->slab; continue; }
+                if (cudaIpcOpenMemHandle(&h->peer_slab[p], all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError(); h->peer_slab[p] = nullptr; okp = false;
+                }
+            }
+            // all ranks must agree (0 = everybody mapped everybody)
+            int bad = okp ? 0 : 1;
+            CKC(cudaMemcpyAsync(h->bar_dev + 1, &bad, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            r2 = g_nccl.AllReduce(h->bar_dev + 1, h->bar_dev + 1, 1, ncclInt32, ncclMax, h->comm, h->stream);
+            if (r2 != ncclSuccess) { fail("ncclAllReduce failed"); nsb200_destroy(h); return 1; }
+            CKC(cudaMemcpyAsync(&bad, h->bar_dev + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CKC(cudaStreamSynchronize(h->stream));
+            h->p2p = (bad == 0);
+            if (h->p2p)
+                for (int p = 0; p < n_ranks; ++p)
+                    h->peer_delta[p] = (long long)((char*)h->peer_slab[p] - (char*)h->slab);
+        }
     }
     CKC(cudaStreamSynchronize(h->stream));
 #undef CKC
@@ -636,8 +724,9 @@ int nsb200_nonlinear_rhs(nsb200_ctx* h, const double* u_hat_in, double* dw_hat_d
     CKR(set_device(h));
     CKR(upload_to(h, u_hat_in, h->TMP));
     int crs = 0;
-    CKR(rhs_raw(h, h->TMP, false, &crs));   // arbitrary input: no assumption on its support
-    CKR(rk_stage(h, 4, 0.0, crs, false));   // normalise + project + dealias -> ACC
+    cplx** c = nullptr;
+    CKR(rhs_raw(h, h->TMP, false, &crs, &c));   // arbitrary input: no assumption on its support
+    CKR(rk_stage(h, 4, 0.0, crs, false, c));    // normalise + project + dealias -> ACC
     return download_from(h, dw_hat_dt_out, h->ACC);
 }
 
@@ -866,7 +955,7 @@ int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_
             case NSB200_OP_PASS_X: CKR(run_pass_full(h, 'x', INV, 3, h->W, h->W)); break;
             case NSB200_OP_PASS_Z: CKR(run_z(h, NSB_Z_C2R, 3, h->W, h->nzp, h->nzf, h->nzf)); break;
             case NSB200_OP_Z_FUSED: CKR(run_z(h, NSB_Z_FUSED, 3, h->W, h->nzp, h->nzf, h->nzf)); break;
-            case NSB200_OP_RK_POINTWISE: CKR(rk_stage(h, 1, dt, h->nzp, false)); break;
+            case NSB200_OP_RK_POINTWISE: CKR(rk_stage(h, 1, dt, h->nzp, false, h->R)); break;
             case NSB200_OP_L2_FLUSH: CK(cudaMemsetAsync(h->flush_buf, it & 0xff, h->flush_bytes, h->stream)); break;
             default: return fail("nsb200_time_op: unknown op");
         }

@@ -44,7 +44,7 @@ def workload_config(n, n_gpus):
         "workload": "random-phase decaying turbulence %d^3 FP64 RK4 (BASELINE.json configs[2]; E(k)~k^4 exp(-2(k/4)^2), E=pi^3)" % n,
         "N": n, "nu": NU, "dt": DT, "ic": "RANDOM_PHASE seed=%d kp=%g" % (SEED, KP),
         "dealias": "2/3 spherical, integer threshold N/3", "viscosity": "nu k^2 (CN factor in the final update)",
-        "parallelism": "kx slabs x %d, NCCL all-to-all inside each 3-D transform" % n_gpus if n_gpus > 1 else "single GPU",
+        "parallelism": "kx slabs x %d; slab all-to-all fused into the FFT store phase (peer stores over NVLink, CUDA IPC), NCCL for barriers/diagnostics" % n_gpus if n_gpus > 1 else "single GPU",
         "l2": "no flush: every pass streams fields of %.2f GB each (>> 126 MB L2)" % (scalar_bytes(n) / 1e9),
     }
 

