@@ -59,6 +59,8 @@ struct StridedArgs {
     // slab allocation to rank r's (CUDA IPC mapping; 0 for r == self), out_s1 is not used and dst[] already
     // includes this rank's block offset inside the receiver's buffer.
     int out_p2p;
+    int out_rank_lo;    // p2p: destination rank = n & out_mask, local index = n >> out_shift (cyclic kx planes)
+                        //      instead of rank = n >> out_shift, local index = n & out_mask (contiguous y slabs)
     long long peer_delta[NSB_MAX_PEERS];
 };
 
@@ -104,8 +106,9 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a) {
                 for (int k2 = 0; k2 < P::RL; ++k2) {
                     const int n = b + k2 * P::NBL;
                     if (!(n >= slo && n < shi)) {
-                        cplx* d = reinterpret_cast<cplx*>(reinterpret_cast<char*>(dst) + s_delta[n >> osh]);
-                        d[(long long)(n & omk) * os2] = v[k2];
+                        const int hi = n >> osh, lo = n & omk;
+                        cplx* d = reinterpret_cast<cplx*>(reinterpret_cast<char*>(dst) + s_delta[a.out_rank_lo ? lo : hi]);
+                        d[(long long)(a.out_rank_lo ? hi : lo) * os2] = v[k2];
                     }
                 }
             }

@@ -140,6 +140,7 @@ struct nsb200_ctx {
     void* peer_slab[NSB_MAX_PEERS] = {nullptr};   // CUDA IPC mappings of every rank's slab allocation (self = own pointer)
     long long peer_delta[NSB_MAX_PEERS] = {0};
     bool p2p = false;                              // slab exchange fused into the FFT store phase over NVLink
+    bool cyclic = false;                           // kx planes distributed cyclically (plane g on rank g % P) for load balance
     int* bar_dev = nullptr;
     int sm_count = 0;
     int zgrid[3] = {0, 0, 0};
@@ -150,7 +151,14 @@ struct nsb200_ctx {
     double prof_bytes[NSB200_PC_COUNT] = {0};   // algorithmic (minimal) bytes of the launches recorded, per class
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
-    Geom geom(bool windowed = false) const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.x_start = x_start; g.kcut = windowed ? kmax : N; return g; }
+    // device distribution of the kx planes (cyclic when the peer mapping is available)
+    Geom geom(bool windowed = false) const {
+        Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.kcut = windowed ? kmax : N;
+        g.x_start = cyclic ? rank : x_start; g.x_stride = cyclic ? nranks : 1;
+        return g;
+    }
+    // the boundary's contiguous slab (fftw_mpi_local_size_many)
+    Geom geom_api() const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.kcut = N; g.x_start = x_start; g.x_stride = 1; return g; }
     long long nrows() const { return (long long)nx_loc * N; }
     int row_grid() const { long long r = nrows(); long long cap = (long long)sm_count * 32; return (int)(r < cap ? r : cap); }
 };
@@ -218,7 +226,9 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
     if (ps.axis == 'y') {
         n_outer = h->nx_loc;
         if (ps.outer_w) {   // local kx planes with global index in [K+1, N-K) carry nothing
-            int lo = K + 1 - h->x_start, hi = N - K - h->x_start;
+            // global index of local plane i: x0 + i*xs ; first i above K, first i at or above N-K
+            const int x0 = h->cyclic ? h->rank : h->x_start, xs = h->cyclic ? h->nranks : 1;
+            int lo = (K - x0 >= 0) ? (K - x0) / xs + 1 : 0, hi = (N - K - x0 > 0) ? (N - K - x0 + xs - 1) / xs : 0;
             lo = lo < 0 ? 0 : (lo > h->nx_loc ? h->nx_loc : lo);
             hi = hi < 0 ? 0 : (hi > h->nx_loc ? h->nx_loc : hi);
             if (hi > lo) { a.outer_lo = lo; a.outer_hi = hi; n_outer -= hi - lo; }
@@ -244,7 +254,29 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         n_outer = h->ny_loc;
         a.in_so = ps.in_rs;  a.in_s2 = (long long)h->ny_loc * ps.in_rs;
         a.out_so = ps.out_rs; a.out_s2 = (long long)h->ny_loc * ps.out_rs;
-        if (ps.p2p_out) {
+        if (h->cyclic) {
+            // the received blocks are [source rank r][local plane li][y_loc][rs] and hold kx = li*P + r
+            long L[5];
+            int lp = 0;
+            while ((1 << lp) < h->nranks) ++lp;
+            if (ps.dir == INV) {      // kx is the INPUT axis: n -> (n & (P-1)) * block + (n >> lp) * plane
+                exchange_layout(N, h->nranks, ps.in_rs, L);
+                a.in_shift = lp; a.in_mask = h->nranks - 1; a.in_s1 = (long long)h->ny_loc * ps.in_rs; a.in_s2 = L[2];
+            } else if (!ps.p2p_out) { // forward, NCCL exchange: same layout on the OUTPUT side
+                exchange_layout(N, h->nranks, ps.out_rs, L);
+                a.out_shift = lp; a.out_mask = h->nranks - 1; a.out_s1 = (long long)h->ny_loc * ps.out_rs; a.out_s2 = L[2];
+            }
+        }
+        if (ps.p2p_out && h->cyclic) {
+            long L[5];
+            int lp = 0;
+            while ((1 << lp) < h->nranks) ++lp;
+            exchange_layout(N, h->nranks, ps.out_rs, L);
+            a.out_p2p = 1; a.out_rank_lo = 1; a.out_shift = lp; a.out_mask = h->nranks - 1; a.out_s1 = 0;
+            a.out_s2 = (long long)h->ny_loc * ps.out_rs;   // local plane stride in the receiver's block
+            for (int f = 0; f < field_cnt; ++f) a.dst[f] += (long long)h->rank * L[2];
+            for (int r = 0; r < h->nranks; ++r) a.peer_delta[r] = h->peer_delta[r];
+        } else if (ps.p2p_out) {
             // forward x pass: output plane kx belongs to rank kx / nx_loc; it lands in that rank's buffer at
             // [this rank (y-slab owner)][kx_loc][y_loc][rs], the input layout of the forward y pass
             long L[5];
@@ -491,6 +523,14 @@ int nsb200_exchange_layout(long N, int n_ranks, long row_stride, long out[5]) {
     return 0;
 }
 
+int nsb200_plane_owner(long N, int n_ranks, int cyclic, long kx_index, int* rank, long* local_index) {
+    if (n_ranks < 1 || N < 1 || N % n_ranks != 0 || kx_index < 0 || kx_index >= N || !rank || !local_index)
+        return fail("nsb200_plane_owner: bad argument");
+    if (cyclic) { *rank = (int)(kx_index % n_ranks); *local_index = kx_index / n_ranks; }
+    else { *rank = (int)(kx_index / (N / n_ranks)); *local_index = kx_index % (N / n_ranks); }
+    return 0;
+}
+
 int nsb200_get_nccl_unique_id(void* out128) {
     CKR(load_nccl());
     ncclUniqueId id;
@@ -652,6 +692,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
             CKC(cudaMemcpyAsync(&bad, h->bar_dev + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CKC(cudaStreamSynchronize(h->stream));
             h->p2p = (bad == 0);
+            { const char* nc = getenv("NSB200_NO_CYCLIC"); h->cyclic = h->p2p && !(nc && nc[0] == '1'); }
             if (h->p2p)
                 for (int p = 0; p < n_ranks; ++p)
                     h->peer_delta[p] = (long long)((char*)h->peer_slab[p] - (char*)h->slab);
@@ -673,10 +714,23 @@ long nsb200_local_fourier_elems(nsb200_ctx* h) { return h ? 3L * h->nx_loc * h->
 long nsb200_launch_count(nsb200_ctx* h) { return h ? h->launches : 0; }
 long nsb200_device_bytes(nsb200_ctx* h) { return h ? (long)h->bytes : 0; }
 
+static PeerTable peer_table(const nsb200_ctx* h) {
+    PeerTable pt;
+    for (int r = 0; r < NSB_MAX_PEERS; ++r) pt.delta[r] = h->peer_delta[r];
+    return pt;
+}
 static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
     const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
     cplx* stage = h->W[0];   // W is one contiguous 6-field buffer >= the 3-field host layout
     CK(cudaMemcpyAsync(stage, host, n * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    if (h->cyclic) {
+        CKR(gpu_barrier(h));   // nobody still reads the destination arrays
+        k_aos_to_planar_scatter<<<h->row_grid(), 128, 0, h->stream>>>(stage, dst[0], dst[1], dst[2], h->geom_api(), h->x_start, h->nranks, peer_table(h));
+        CK(cudaGetLastError());
+        h->launches++;
+        CKR(gpu_barrier(h));   // every rank's planes have landed
+        return 0;
+    }
     k_aos_to_planar<<<h->row_grid(), 128, 0, h->stream>>>(stage, dst[0], dst[1], dst[2], h->geom(), h->nrows());
     CK(cudaGetLastError());
     h->launches++;
@@ -685,9 +739,17 @@ static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
 static int download_from(nsb200_ctx* h, double* host, cplx* const* src) {
     const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
     cplx* stage = h->W[0];
-    k_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, src[0], src[1], src[2], h->geom(), h->nrows());
-    CK(cudaGetLastError());
-    h->launches++;
+    if (h->cyclic) {
+        CKR(gpu_barrier(h));   // every rank's source arrays are final
+        k_planar_to_aos_gather<<<h->row_grid(), 128, 0, h->stream>>>(stage, src[0], src[1], src[2], h->geom_api(), h->x_start, h->nranks, peer_table(h));
+        CK(cudaGetLastError());
+        h->launches++;
+        CKR(gpu_barrier(h));   // nobody overwrites them before all gathers are done
+    } else {
+        k_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, src[0], src[1], src[2], h->geom(), h->nrows());
+        CK(cudaGetLastError());
+        h->launches++;
+    }
     CK(cudaMemcpyAsync(host, stage, n * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -738,7 +800,7 @@ int nsb200_apply_dealiasing(nsb200_ctx* h, double* array_host, int array_dim) {
     cplx* stage = h->W[0];
     CK(cudaMemcpyAsync(stage, array_host, n * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
     if (h->dealias == NSB200_DEALIAS_23) {
-        k_dealias_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, array_dim, h->geom(), h->kmax2, h->nrows());
+        k_dealias_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, array_dim, h->geom_api(), h->kmax2, h->nrows());
         CK(cudaGetLastError());
         h->launches++;
     }

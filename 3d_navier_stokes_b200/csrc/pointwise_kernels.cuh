@@ -14,6 +14,7 @@ struct Geom {
     int nzp;      // row stride (complex elements) of the planar device fields
     int nx_loc;   // local number of kx planes (slab)
     int x_start;  // global index of the first local kx plane
+    int x_stride; // global index distance between consecutive local planes (1: contiguous slab; P: cyclic)
     int kcut;     // support window: only |kx|, |ky| <= kcut and kz <= kcut are touched (kcut >= N: everything)
 };
 
@@ -58,6 +59,53 @@ __global__ void k_planar_to_aos(cplx* __restrict__ aos, const cplx* p0, const cp
         }
     }
 }
+// Multi-GPU boundary: the host slab is contiguous in kx (fftw_mpi_local_size_many), the device distribution is
+// cyclic (plane g lives on rank g % P at local index g / P) so that every rank owns an equal share of the
+// dealiased support.  Upload scatters the planes straight into the owners' memory, download gathers them.
+struct PeerTable { long long delta[NSB_MAX_PEERS]; };
+__global__ void k_aos_to_planar_scatter(const cplx* __restrict__ aos, cplx* p0, cplx* p1, cplx* p2, Geom g, int api_start,
+                                        int nranks, PeerTable pt) {
+    __shared__ long long s_delta[NSB_MAX_PEERS];
+    if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = pt.delta[threadIdx.x];
+    __syncthreads();
+    const long long nrows = (long long)g.nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int gidx = api_start + i, owner = gidx % nranks, li = gidx / nranks;
+        const long long drow = ((long long)li * g.N + j) * g.nzp;
+        const cplx* src = aos + row * g.nzf * 3;
+        cplx* d0 = reinterpret_cast<cplx*>(reinterpret_cast<char*>(p0) + s_delta[owner]) + drow;
+        cplx* d1 = reinterpret_cast<cplx*>(reinterpret_cast<char*>(p1) + s_delta[owner]) + drow;
+        cplx* d2 = reinterpret_cast<cplx*>(reinterpret_cast<char*>(p2) + s_delta[owner]) + drow;
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            d0[k] = src[3 * k + 0];
+            d1[k] = src[3 * k + 1];
+            d2[k] = src[3 * k + 2];
+        }
+    }
+}
+__global__ void k_planar_to_aos_gather(cplx* __restrict__ aos, const cplx* p0, const cplx* p1, const cplx* p2, Geom g, int api_start,
+                                       int nranks, PeerTable pt) {
+    __shared__ long long s_delta[NSB_MAX_PEERS];
+    if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = pt.delta[threadIdx.x];
+    __syncthreads();
+    const long long nrows = (long long)g.nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int gidx = api_start + i, owner = gidx % nranks, li = gidx / nranks;
+        const long long srow = ((long long)li * g.N + j) * g.nzp;
+        cplx* dst = aos + row * g.nzf * 3;
+        const cplx* s0 = reinterpret_cast<const cplx*>(reinterpret_cast<const char*>(p0) + s_delta[owner]) + srow;
+        const cplx* s1 = reinterpret_cast<const cplx*>(reinterpret_cast<const char*>(p1) + s_delta[owner]) + srow;
+        const cplx* s2 = reinterpret_cast<const cplx*>(reinterpret_cast<const char*>(p2) + s_delta[owner]) + srow;
+        for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
+            dst[3 * k + 0] = s0[k];
+            dst[3 * k + 1] = s1[k];
+            dst[3 * k + 2] = s2[k];
+        }
+    }
+}
+
 // real fields: host [x][y][Nz+2][3] doubles (solver.c:667-672) <-> planar rows of 2*nzp doubles
 __global__ void k_real_aos_to_planar(const double* __restrict__ aos, double* p0, double* p1, double* p2, Geom g, long long nrows) {
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
@@ -93,7 +141,7 @@ __global__ void k_curl(const CurlArgs a) {
     const long long nrows = (long long)g.nx_loc * g.N;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
-        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         if (!nsb_in_window(kx, ky, g.kcut)) continue;
         const long long base = row * g.nzp, wbase = row * a.w_rs;
         const int nk = nsb_kz_count(g);
@@ -154,7 +202,7 @@ __global__ void k_rk_stage(const RkArgs a) {
     const long long nrows = (long long)g.nx_loc * g.N;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
-        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         const long long base = row * g.nzp, cbase = row * a.c_rs;
         const bool row_in = nsb_in_window(kx, ky, g.kcut);
         if (!row_in && a.skip_outside) continue;
@@ -211,7 +259,7 @@ __global__ void k_rk_stage(const RkArgs a) {
 __global__ void k_dealias_aos(cplx* arr, int dim, Geom g, int kmax2, long long nrows) {
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
-        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
             if (kx * kx + ky * ky + k * k > kmax2)
                 for (int l = 0; l < dim; ++l) arr[(row * g.nzf + k) * dim + l] = mk(0.0, 0.0);
@@ -222,7 +270,7 @@ __global__ void k_dealias_planar(cplx* p0, cplx* p1, cplx* p2, Geom g, int kmax2
     const long long nrows = (long long)g.nx_loc * g.N;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
-        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
             if (kx * kx + ky * ky + k * k > kmax2) {
                 p0[row * g.nzp + k] = mk(0.0, 0.0);
@@ -248,7 +296,7 @@ __global__ void k_check_support(const cplx* p0, const cplx* p1, const cplx* p2, 
     int bad = 0;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
-        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         const bool row_in = nsb_in_window(kx, ky, kcut);
         for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
             if (row_in && k <= kcut) continue;
@@ -282,7 +330,7 @@ __global__ void __launch_bounds__(256) k_measure(const MeasArgs a) {
     for (int m = 0; m < NSB_NMEAS; ++m) acc[m] = 0.0;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
-        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         const long long base = row * g.nzp;
         for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
             const cplx ux = a.u[0][base + k], uy = a.u[1][base + k], uz = a.u[2][base + k];
@@ -351,7 +399,7 @@ __global__ void __launch_bounds__(256) k_spectra(const SpectArgs a) {
     const long long nrows = (long long)g.nx_loc * g.N;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
-        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         const long long base = row * g.nzp;
         for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
             const cplx ux = a.u[0][base + k], uy = a.u[1][base + k], uz = a.u[2][base + k];
@@ -436,7 +484,7 @@ __global__ void k_ic_random_phase(const RandArgs a) {
     const long long nrows = (long long)g.nx_loc * g.N;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
-        const int kx = nsb_wavenum(g.x_start + i, g.N), ky = nsb_wavenum(j, g.N);
+        const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         for (int kz = threadIdx.x; kz < g.nzf; kz += blockDim.x) {
             const long long e = row * g.nzp + kz;
             const int k2i = kx * kx + ky * ky + kz * kz;

@@ -68,6 +68,13 @@ int nsb200_get_nccl_unique_id(void* out128);
  * fftw_mpi_execute_dft_* (solver.c:656-683). */
 int nsb200_exchange_layout(long N, int n_ranks, long row_stride, long out[5]);
 
+/* Device-side ownership of Fourier plane kx_index.  The boundary keeps the reference's contiguous slabs
+ * (rank = kx / (N/P)); inside the library the planes are dealt out cyclically (rank = kx % P, local index
+ * kx / P) when the peer mapping is available, so that every rank owns an equal share of the dealiased support
+ * (contiguous slabs leave the ranks that own |kx| > N/3 idle in the Fourier-side passes).  Upload / download
+ * redistribute over NVLink.  After the exchange the block received from rank r holds planes kx = li*P + r. */
+int nsb200_plane_owner(long N, int n_ranks, int cyclic, long kx_index, int* rank, long* local_index);
+
 /* sys_vars->local_Nx / local_Nx_start as fftw_mpi_local_size_many reports them (solver.c:1845). */
 int nsb200_local_slab(nsb200_ctx* h, long* local_nx, long* local_nx_start);
 /* Number of double _Complex elements of a local Fourier vector field (= alloc_local_batch). */

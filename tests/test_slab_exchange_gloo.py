@@ -20,7 +20,7 @@ capi = importlib.import_module("3d_navier_stokes_b200.capi")
 pytestmark = pytest.mark.skipif(not os.path.exists(capi.lib_path()), reason="libnsb200.so not built")
 
 
-def _worker(rank, world, n, rs, port, q):
+def _worker(rank, world, n, rs, port, q, cyclic):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -33,7 +33,15 @@ def _worker(rank, world, n, rs, port, q):
         nx_loc = ny_loc = n // world
         rng = np.random.default_rng(1234)                      # same global field on every rank
         glob = rng.standard_normal((n, n, nzf)) + 1j * rng.standard_normal((n, n, nzf))
-        mine = glob[rank * nx_loc:(rank + 1) * nx_loc]        # Fourier slab [kx_loc][ky][kz]
+        # which global planes this rank owns on the device (contiguous slab, or dealt out cyclically)
+        owner = np.empty(n, dtype=np.int64); local = np.empty(n, dtype=np.int64)
+        for gk in range(n):
+            r_, l_ = ctypes.c_int(), ctypes.c_long()
+            assert lib.nsb200_plane_owner(n, world, cyclic, gk, ctypes.byref(r_), ctypes.byref(l_)) == 0
+            owner[gk], local[gk] = r_.value, l_.value
+        my_planes = np.array(sorted(np.nonzero(owner == rank)[0], key=lambda gk: local[gk]))
+        assert len(my_planes) == nx_loc
+        mine = glob[my_planes]                                 # Fourier planes of this rank [kx_loc][ky][kz]
         ypass = np.fft.ifft(mine, axis=1) * n                  # unnormalised inverse along y
         send = np.zeros(world * block, dtype=np.complex128)
         i, y, k = np.meshgrid(np.arange(nx_loc), np.arange(n), np.arange(nzf), indexing="ij")
@@ -41,14 +49,19 @@ def _worker(rank, world, n, rs, port, q):
         recv = np.empty_like(send)
         ts, tr = torch.from_numpy(send.view(np.float64)), torch.from_numpy(recv.view(np.float64))
         dist.all_to_all_single(tr, ts)
-        got = recv.reshape(n, ny_loc, rs)[:, :, :nzf]         # [kx][y_loc][kz]
+        blocks = recv.reshape(world, nx_loc, ny_loc, rs)[:, :, :, :nzf]    # [source rank][local plane][y_loc][kz]
+        got = np.empty((n, ny_loc, nzf), dtype=np.complex128)               # [kx][y_loc][kz]
+        for gk in range(n):
+            got[gk] = blocks[owner[gk], local[gk]]
         xpass = np.fft.ifft(got, axis=0) * n
         ref = np.fft.ifft2(glob, axes=(0, 1)) * n * n
         err = np.abs(xpass - ref[:, rank * ny_loc:(rank + 1) * ny_loc, :]).max() / np.abs(ref).max()
         # reverse direction: forward x pass, exchange back, forward y pass with the layout on the INPUT side
         fx = np.fft.fft(xpass, axis=0)                         # [kx][y_loc][kz]
         back_send = np.zeros(world * block, dtype=np.complex128)
-        back_send.reshape(n, ny_loc, rs)[:, :, :nzf] = fx      # block r = kx planes of rank r: already contiguous
+        bs = back_send.reshape(world, nx_loc, ny_loc, rs)
+        for gk in range(n):                                    # block r = the kx planes rank r owns
+            bs[owner[gk], local[gk], :, :nzf] = fx[gk]
         back_recv = np.empty_like(back_send)
         dist.all_to_all_single(torch.from_numpy(back_recv.view(np.float64)), torch.from_numpy(back_send.view(np.float64)))
         gathered = back_recv[(y >> shift) * block + i * outer + (y & mask) * row + k]   # [kx_loc][y][kz]
@@ -59,12 +72,12 @@ def _worker(rank, world, n, rs, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,rs", [(2, 16, 16), (2, 32, 24), (4, 16, 9)])
-def test_slab_exchange_layout_over_gloo(world, n, rs):
+@pytest.mark.parametrize("world,n,rs,cyclic", [(2, 16, 16, 0), (2, 32, 24, 1), (4, 16, 9, 1)])
+def test_slab_exchange_layout_over_gloo(world, n, rs, cyclic):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + world * 10 + n % 7
-    procs = [ctx.Process(target=_worker, args=(r, world, n, rs, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, n, rs, port, q, cyclic)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in range(world)]
