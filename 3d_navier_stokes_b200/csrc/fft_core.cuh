@@ -121,7 +121,7 @@ template <int DIR> struct Dft<16, DIR> {
 // ---------------------------------------------------------------------------------------------
 // Plans: N = R1 * R2 * R3 (R3 == 1 for two-pass plans)
 // ---------------------------------------------------------------------------------------------
-template <int N_, int R1_, int R2_, int R3_> struct FftPlan {
+template <int N_, int R1_, int R2_, int R3_, int PAD_ = 1> struct FftPlan {
     static constexpr int N = N_, R1 = R1_, R2 = R2_, R3 = R3_;
     static constexpr int PASSES = (R3_ > 1) ? 3 : 2;
     static constexpr int M1 = N_ / R1_;                  // row length after pass 1
@@ -129,19 +129,21 @@ template <int N_, int R1_, int R2_, int R3_> struct FftPlan {
     static constexpr int NB1 = N_ / R1_;                 // butterflies per pass
     static constexpr int NB2 = N_ / R2_;
     static constexpr int NBL = N_ / RL;
-    static constexpr int NPAD = N_ + R1_;                // padded shared-memory elements per transform
+    static constexpr int ROW = N_ / R1_ + PAD_;          // shared-memory row pitch (PAD_ = 0 for tile-interleaved buffers,
+                                                         // which are conflict free without padding and can be filled in place)
+    static constexpr int NPAD = R1_ * ROW;               // shared-memory elements per transform
     static_assert(R1_ * R2_ * R3_ == N_, "bad plan");
 };
 
 // throughput plans (strided x / y passes): large radices, few passes
 template <int N> struct BigPlan;
-template <> struct BigPlan<16> { typedef FftPlan<16, 4, 4, 1> type; };
-template <> struct BigPlan<32> { typedef FftPlan<32, 4, 8, 1> type; };
-template <> struct BigPlan<64> { typedef FftPlan<64, 8, 8, 1> type; };
-template <> struct BigPlan<128> { typedef FftPlan<128, 8, 16, 1> type; };
-template <> struct BigPlan<256> { typedef FftPlan<256, 16, 16, 1> type; };
-template <> struct BigPlan<512> { typedef FftPlan<512, 8, 8, 8> type; };
-template <> struct BigPlan<1024> { typedef FftPlan<1024, 8, 8, 16> type; };
+template <> struct BigPlan<16> { typedef FftPlan<16, 4, 4, 1, 0> type; };
+template <> struct BigPlan<32> { typedef FftPlan<32, 4, 8, 1, 0> type; };
+template <> struct BigPlan<64> { typedef FftPlan<64, 8, 8, 1, 0> type; };
+template <> struct BigPlan<128> { typedef FftPlan<128, 8, 16, 1, 0> type; };
+template <> struct BigPlan<256> { typedef FftPlan<256, 16, 16, 1, 0> type; };
+template <> struct BigPlan<512> { typedef FftPlan<512, 8, 8, 8, 0> type; };
+template <> struct BigPlan<1024> { typedef FftPlan<1024, 8, 8, 16, 0> type; };
 
 // z-pencil plans: R1 is the smallest radix so pass 1 has exactly one butterfly per thread with
 // TP = N/R1 threads per transform (later passes use a subset of the threads)
@@ -164,7 +166,7 @@ template <> struct ZFPlan<256> { typedef FftPlan<256, 8, 4, 8> type; };
 template <> struct ZFPlan<512> { typedef FftPlan<512, 8, 8, 8> type; };
 template <> struct ZFPlan<1024> { typedef FftPlan<1024, 16, 4, 16> type; };
 
-template <class P> NSB_HD int padi(int i) { return i + i / P::M1; }
+template <class P> NSB_HD int padi(int i) { return (i / P::M1) * P::ROW + i % P::M1; }
 
 // ---------------------------------------------------------------------------------------------
 // Passes.  `sm` points at element 0 of this transform's shared-memory buffer, STRIDE is the distance
@@ -179,7 +181,21 @@ NSB_HD void fft_pass1(int b, cplx* sm, const cplx* __restrict__ tw, Ld ld) {
 #pragma unroll
     for (int k1 = 1; k1 < P::R1; ++k1) v[k1] = cmul(v[k1], twid<DIR>(tw, b * k1));
 #pragma unroll
-    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * (P::M1 + 1) + b) * STRIDE] = v[k1];
+    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * P::ROW + b) * STRIDE] = v[k1];
+}
+
+// pass 1 on a transform already sitting in shared memory in natural order (unpadded plans): in place, no barrier
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass1_inplace(int b, cplx* sm, const cplx* __restrict__ tw) {
+    static_assert(P::ROW == P::M1, "in-place pass 1 needs an unpadded plan");
+    cplx v[P::R1];
+#pragma unroll
+    for (int j = 0; j < P::R1; ++j) v[j] = sm[(b + j * P::M1) * STRIDE];
+    Dft<P::R1, DIR>::run(v);
+#pragma unroll
+    for (int k1 = 1; k1 < P::R1; ++k1) v[k1] = cmul(v[k1], twid<DIR>(tw, b * k1));
+#pragma unroll
+    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * P::ROW + b) * STRIDE] = v[k1];
 }
 
 // pass 1 on values already in registers (used when the loader needs a barrier before the scatter)
@@ -190,14 +206,14 @@ template <class P, int DIR> NSB_HD void fft_pass1_regs(int b, cplx* v, const cpl
 }
 template <class P, int STRIDE> NSB_HD void fft_pass1_scatter(int b, cplx* sm, const cplx* v) {
 #pragma unroll
-    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * (P::M1 + 1) + b) * STRIDE] = v[k1];
+    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * P::ROW + b) * STRIDE] = v[k1];
 }
 
 template <class P, int DIR, int STRIDE>
 NSB_HD void fft_pass2(int b, cplx* sm, const cplx* __restrict__ tw) {
     static_assert(P::PASSES == 3, "pass2 only exists in 3-pass plans");
     const int k1 = b / P::R3, m2 = b % P::R3;
-    const int base = k1 * (P::M1 + 1) + m2;
+    const int base = k1 * P::ROW + m2;
     cplx v[P::R2];
 #pragma unroll
     for (int j = 0; j < P::R2; ++j) v[j] = sm[(base + j * P::R3) * STRIDE];
@@ -231,7 +247,7 @@ NSB_HD void fft_pass1_rw(int b, cplx* sm, const cplx* w, Ld ld) {
 #pragma unroll
     for (int k1 = 1; k1 < P::R1; ++k1) v[k1] = cmul_dir<DIR>(v[k1], w[k1 - 1]);
 #pragma unroll
-    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * (P::M1 + 1) + b) * STRIDE] = v[k1];
+    for (int k1 = 0; k1 < P::R1; ++k1) sm[(k1 * P::ROW + b) * STRIDE] = v[k1];
 }
 template <class P, int DIR> NSB_HD void fft_pass1_regs_rw(cplx* v, const cplx* w) {
     Dft<P::R1, DIR>::run(v);
@@ -242,7 +258,7 @@ template <class P, int DIR, int STRIDE>
 NSB_HD void fft_pass2_rw(int b, cplx* sm, const cplx* w) {
     static_assert(P::PASSES == 3, "pass2 only exists in 3-pass plans");
     const int k1 = b / P::R3, m2 = b % P::R3;
-    const int base = k1 * (P::M1 + 1) + m2;
+    const int base = k1 * P::ROW + m2;
     cplx v[P::R2];
 #pragma unroll
     for (int j = 0; j < P::R2; ++j) v[j] = sm[(base + j * P::R3) * STRIDE];
@@ -257,7 +273,7 @@ NSB_HD void fft_pass2_rw(int b, cplx* sm, const cplx* w) {
 template <class P, int DIR, int STRIDE>
 NSB_HD void fft_pass_last(int b, const cplx* sm, cplx* v) {
     const int k1 = b % P::R1, kp = b / P::R1;
-    const int base = k1 * (P::M1 + 1) + kp * P::RL;
+    const int base = k1 * P::ROW + kp * P::RL;
 #pragma unroll
     for (int m = 0; m < P::RL; ++m) v[m] = sm[(base + m) * STRIDE];
     Dft<P::RL, DIR>::run(v);

@@ -85,12 +85,32 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a) {
     const int ish = a.in_shift, imk = a.in_mask, osh = a.out_shift, omk = a.out_mask;
     const int zlo = a.in_zero_lo, zhi = a.in_zero_hi;
 
+#if defined(__CUDA_ARCH__) && !defined(NSB_STRIDED_NO_ASYNC)
+    // Whole tile in flight at once: every thread issues its N/TP 16-byte asynchronous copies (L2 only, zero fill
+    // for known-zero rows and out-of-range columns), then the CTA transforms the tile in place.  While one CTA
+    // waits for its tile the other resident CTAs compute.
+    {
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+#pragma unroll 4
+        for (int n = q; n < P::N; n += TP) {
+            const bool live = valid && !(n >= zlo && n < zhi);
+            const cplx* g = live ? src + ((long long)(n >> ish) * is1 + (long long)(n & imk) * is2) : a.tw;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + (unsigned)(n * T) * 16u), "l"(g), "r"(live ? 16 : 0));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    for (int b = q; b < P::NB1; b += TP) fft_pass1_inplace<P, DIR, T>(b, sm, tw);
+    __syncthreads();
+#else
     for (int b = q; b < P::NB1; b += TP) {
         fft_pass1<P, DIR, T>(b, sm, tw, [&](int n) {
             return (valid && !(n >= zlo && n < zhi)) ? NSB_LDCG(src + ((long long)(n >> ish) * is1 + (long long)(n & imk) * is2)) : mk(0.0, 0.0);
         });
     }
     __syncthreads();
+#endif
     if constexpr (P::PASSES == 3) {
         for (int b = q; b < P::NB2; b += TP) fft_pass2<P, DIR, T>(b, sm, tw);
         __syncthreads();
@@ -276,7 +296,7 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
     const cplx* __restrict__ tw = a.tw;
     const int kzin = a.kz_in, kzout = a.kz_out;
     // this thread's row in the in-place layout (same indexing as fft_pass_last with b = q)
-    const int rowbase = (q % P::R1) * (P::M1 + 1) + (q / P::R1) * P::RL;
+    const int rowbase = (q % P::R1) * P::ROW + (q / P::R1) * P::RL;
     // Loop-invariant twiddles of this thread live in registers: in this kernel every lane needs different
     // table entries, so fetching them per pass cost more L1 cycles than the data exchange (profiles/).
     constexpr bool RW2 = (P::PASSES == 3) && (P::NB2 == TP);   // one pass-2 butterfly per thread
@@ -365,7 +385,7 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
                 if (k <= N / 2 && k < kzout) {
                     const int m = (N - k) & (N - 1);          // partner Z(N - k) sits in the row of thread m % NBL
                     const int qm = m % P::NBL, jm = m / P::NBL;
-                    const cplx Zm = buf[(qm % P::R1) * (P::M1 + 1) + (qm / P::R1) * P::RL + jm];
+                    const cplx Zm = buf[(qm % P::R1) * P::ROW + (qm / P::R1) * P::RL + jm];
                     cplx A, B;
                     unpack_pair(v[j], Zm, A, B);
                     ra[k] = A;

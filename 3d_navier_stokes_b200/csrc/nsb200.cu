@@ -161,6 +161,8 @@ struct nsb200_ctx {
     Geom geom_api() const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.kcut = N; g.x_start = x_start; g.x_stride = 1; return g; }
     long long nrows() const { return (long long)nx_loc * N; }
     int row_grid() const { long long r = nrows(); long long cap = (long long)sm_count * 32; return (int)(r < cap ? r : cap); }
+    // threads per CTA for row kernels that walk nk modes of a row: one trip per row, few idle lanes
+    static int row_block(int nk) { int b = (nk + 31) / 32 * 32; return b < 64 ? 64 : (b > 512 ? 512 : b); }
 };
 
 static int set_device(nsb200_ctx* h) { CK(cudaSetDevice(h->device)); return 0; }
@@ -371,7 +373,7 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx***
     {
         const double kw = in_w ? 2.0 * h->kmax + 1 : h->N;   // kx planes are counted globally / nranks (slab average)
         ProfScope ps(h, NSB200_PC_CURL, 16.0 * 6.0 * (kw * kw / h->nranks) * nz_in);
-        k_curl<<<rg, 128, 0, h->stream>>>(ca);
+        k_curl<<<rg, nsb200_ctx::row_block(nz_in), 0, h->stream>>>(ca);
     }
     CK(cudaGetLastError());
     h->launches++;
@@ -457,7 +459,7 @@ static int rk_stage(nsb200_ctx* h, int stage, double dt, int c_rs, bool in_w, cp
         const double nc = out_w ? (2.0 * h->kmax + 1) * (2.0 * h->kmax + 1) * (h->kmax + 1) / h->nranks : (double)h->nrows() * h->nzf;
         const double arrays = stage == 0 ? 9.0 : stage == 3 ? 9.0 : stage == 4 ? 3.0 : 12.0;   // besides c: u, acc, tmp reads/writes
         ProfScope ps(h, NSB200_PC_RK, 16.0 * (3.0 * nc + arrays * (kw * kw / h->nranks) * nk));
-        k_rk_stage<<<h->row_grid(), 128, 0, h->stream>>>(a);
+        k_rk_stage<<<h->row_grid(), nsb200_ctx::row_block(a.skip_outside ? h->kmax + 1 : h->nzf), 0, h->stream>>>(a);
     }
     CK(cudaGetLastError());
     h->launches++;

@@ -19,7 +19,12 @@ template <class P, int DIR, int STRIDE> double run_plan() {
     }
     for (int i = 0; i < N; ++i) x[i] = mk(frand(), frand());
     cplx* s = sm.data() + (STRIDE > 1 ? 1 : 0);  // pencil p = 1 of an interleaved tile
-    for (int b = 0; b < P::NB1; ++b) fft_pass1<P, DIR, STRIDE>(b, s, tw.data(), [&](int n) { return x[n]; });
+    if constexpr (P::ROW == P::M1) {   // unpadded plan: the strided kernel lands the tile in natural order and runs pass 1 in place
+        for (int i = 0; i < N; ++i) s[(size_t)i * STRIDE] = x[i];
+        for (int b = 0; b < P::NB1; ++b) fft_pass1_inplace<P, DIR, STRIDE>(b, s, tw.data());
+    } else {
+        for (int b = 0; b < P::NB1; ++b) fft_pass1<P, DIR, STRIDE>(b, s, tw.data(), [&](int n) { return x[n]; });
+    }
     if constexpr (P::PASSES == 3)
         for (int b = 0; b < P::NB2; ++b) fft_pass2<P, DIR, STRIDE>(b, s, tw.data());
     for (int b = 0; b < P::NBL; ++b) {
