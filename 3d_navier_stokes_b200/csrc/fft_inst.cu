@@ -19,9 +19,13 @@ constexpr size_t kZFusedSmem = (size_t)6 * ZF::NPAD * ZFusedCfg<ZF>::G * sizeof(
 
 int setup() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_fft_strided<BP, ST, STP, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedSmem);
+    e = cudaFuncSetAttribute(k_fft_strided<BP, ST, STP, FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedSmem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_fft_strided<BP, ST, STP, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedSmem);
+    e = cudaFuncSetAttribute(k_fft_strided<BP, ST, STP, INV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fft_strided<BP, ST, STP, FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fft_strided<BP, ST, STP, INV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_z_c2r<ZP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZSmem);
     if (e != cudaSuccess) return (int)e;
@@ -31,11 +35,17 @@ int setup() {
     return (int)e;
 }
 
-int strided(int dir, const StridedArgs* a, int n_outer_eff, int nfields, cudaStream_t s) {
+int strided(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, cudaStream_t s) {
     dim3 grid((a->nzv + ST - 1) / ST, n_outer_eff, nfields);
     if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
-    if (dir == FWD) k_fft_strided<BP, ST, STP, FWD><<<grid, ST * STP, kStridedSmem, s>>>(*a);
-    else k_fft_strided<BP, ST, STP, INV><<<grid, ST * STP, kStridedSmem, s>>>(*a);
+    static const TmaMaps none = {};
+    if (maps) {
+        if (dir == FWD) k_fft_strided<BP, ST, STP, FWD, true><<<grid, ST * STP, kStridedSmem, s>>>(*a, *maps);
+        else k_fft_strided<BP, ST, STP, INV, true><<<grid, ST * STP, kStridedSmem, s>>>(*a, *maps);
+    } else {
+        if (dir == FWD) k_fft_strided<BP, ST, STP, FWD, false><<<grid, ST * STP, kStridedSmem, s>>>(*a, none);
+        else k_fft_strided<BP, ST, STP, INV, false><<<grid, ST * STP, kStridedSmem, s>>>(*a, none);
+    }
     return (int)cudaGetLastError();
 }
 
@@ -58,4 +68,4 @@ int zocc(int which) {
 }
 }  // namespace
 
-extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G}, setup, strided, zlaunch, zocc};
+extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G}, setup, strided, zlaunch, zocc};

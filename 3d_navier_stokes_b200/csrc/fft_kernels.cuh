@@ -9,6 +9,7 @@
 //                   pencil pair never leave the SM (reference loops solver.c:664-677 between the
 //                   transforms of :656/:658 and :683).
 #pragma once
+#include <cuda.h>
 #include "fft_core.cuh"
 
 #ifdef __CUDA_ARCH__
@@ -34,6 +35,44 @@
 
 #define NSB_MAX_FIELDS 6
 #define NSB_MAX_PEERS 8
+
+// ------------------------------------------------------------------------------ TMA helpers (sm_90+ PTX)
+// One elected thread moves a [rows x T*16 B] pencil tile with cp.async.bulk.tensor; completion is signalled on
+// an mbarrier.  Out-of-bounds rows / columns of the tensor map are zero filled by the hardware, which is how the
+// dealias support pruning (known-zero rows) and the ragged last kz tile are expressed.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void nsb_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void nsb_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nsb_tma_load_3d(unsigned dst, const void* map, int c0, int c1, int c2, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+// bounded wait: a wrong byte count must trap, not hang the GPU
+__device__ __forceinline__ void nsb_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+#endif
+
+// tensor maps of one strided launch: per field a map over the low rows [0, K] (or all rows when the input is not
+// pruned) and one over the high rows [N-K, N)
+struct TmaMaps {
+    CUtensorMap lo[NSB_MAX_FIELDS];
+    CUtensorMap hi[NSB_MAX_FIELDS];
+    int pruned;     // the upper half of the tile comes from `hi`
+    int hi_row0;    // first row covered by `hi` ( = N - K )
+};
+template <int N> struct TmaChunk { static constexpr int ROWS = (N >= 512) ? 256 : N / 2, COUNT = N / ROWS; };
 
 // ------------------------------------------------------------------------------ strided c2c pass
 struct StridedArgs {
@@ -64,9 +103,9 @@ struct StridedArgs {
     long long peer_delta[NSB_MAX_PEERS];
 };
 
-template <class P, int T, int TP, int DIR>
-__global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a) {
-    extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
+template <class P, int T, int TP, int DIR, bool TMA>
+__global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a, const __grid_constant__ TmaMaps maps) {
+    extern __shared__ __align__(1024) unsigned char nsb_smem_raw[];
     cplx* smem = reinterpret_cast<cplx*>(nsb_smem_raw);
     __shared__ long long s_delta[NSB_MAX_PEERS];
     if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = a.peer_delta[threadIdx.x];   // read after the pass barriers
@@ -86,6 +125,29 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a) {
     const int zlo = a.in_zero_lo, zhi = a.in_zero_hi;
 
 #if defined(__CUDA_ARCH__) && !defined(NSB_STRIDED_NO_ASYNC)
+    if constexpr (TMA) {
+        // TMA-staged pencil tile: one thread issues N/ROWS bulk tensor copies of [ROWS x 128 B]; rows outside the
+        // dealiased support and columns beyond the last valid kz are zero filled by the tensor-map bounds.
+        __shared__ __align__(8) unsigned long long s_bar;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+        if (threadIdx.x == 0) nsb_mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            constexpr int ROWS = TmaChunk<P::N>::ROWS, COUNT = TmaChunk<P::N>::COUNT;
+            nsb_mbar_expect_tx(bar, (unsigned)(P::N * T * sizeof(cplx)));
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+#pragma unroll
+            for (int c = 0; c < COUNT; ++c) {
+                const bool use_hi = maps.pruned && (c >= COUNT / 2);
+                const void* mp = use_hi ? (const void*)&maps.hi[field] : (const void*)&maps.lo[field];
+                const int row = use_hi ? c * ROWS - maps.hi_row0 : c * ROWS;
+                nsb_tma_load_3d(sbase + (unsigned)(c * ROWS * T * sizeof(cplx)), mp, (int)(blockIdx.x * T * 2), row, outer, bar);
+            }
+        }
+        nsb_mbar_wait(bar, 0);
+        for (int b = q; b < P::NB1; b += TP) fft_pass1_inplace<P, DIR, T>(b, sm, tw);
+        __syncthreads();
+    } else
     // Whole tile in flight at once: every thread issues its N/TP 16-byte asynchronous copies (L2 only, zero fill
     // for known-zero rows and out-of-range columns), then the CTA transforms the tile in place.  While one CTA
     // waits for its tile the other resident CTAs compute.
@@ -99,10 +161,10 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        for (int b = q; b < P::NB1; b += TP) fft_pass1_inplace<P, DIR, T>(b, sm, tw);
+        __syncthreads();
     }
-    __syncthreads();
-    for (int b = q; b < P::NB1; b += TP) fft_pass1_inplace<P, DIR, T>(b, sm, tw);
-    __syncthreads();
 #else
     for (int b = q; b < P::NB1; b += TP) {
         fft_pass1<P, DIR, T>(b, sm, tw, [&](int n) {

@@ -8,10 +8,12 @@ enum { NSB_Z_C2R = 0, NSB_Z_R2C = 1, NSB_Z_FUSED = 2 };
 struct FftOps {
     int N;
     int strided_T;                 // kz columns per strided tile
+    int tma_rows;                  // rows per TMA box of the strided tile load
     int z_pairs_per_cta[3];        // row pairs per CTA for NSB_Z_C2R / _R2C / _FUSED
     int (*setup)(void);            // opt-in to large dynamic shared memory; returns cudaError_t
     // one c2c pass over `nfields` fields; grid = (ceil(nzv/T), n_outer_eff, nfields)
-    int (*strided)(int dir, const StridedArgs* a, int n_outer_eff, int nfields, cudaStream_t s);
+    // maps != NULL: tile loads through TMA tensor maps (natural layouts); NULL: cp.async path
+    int (*strided)(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, cudaStream_t s);
     // z kernels; grid_x CTAs loop over the row pairs
     int (*z)(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s);
     // resident CTAs per SM of a z kernel (for sizing the persistent grid)

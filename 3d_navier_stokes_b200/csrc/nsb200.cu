@@ -93,6 +93,33 @@ static int load_nccl() {
                         std::to_string(__LINE__) + ")");                                                    \
     } while (0)
 
+// ------------------------------------------------------------------------------ TMA tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int load_tma() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess || !fn || st != cudaDriverEntryPointSuccess)
+        return fail("cuTensorMapEncodeTiled is not available from the driver");
+    g_encode = (EncodeTiledFn)fn;
+    return 0;
+}
+// rank-3 FP64 view of a pencil family: dim0 = 2*cols doubles (contiguous), dim1 = rows (row_stride complex apart),
+// dim2 = outer (outer_stride complex apart); box = [16 doubles][box_rows][1]
+static int encode_map(CUtensorMap* m, const cplx* base, long cols, long rows, long row_stride, long n_outer, long outer_stride, int box_rows) {
+    cuuint64_t dim[3] = {(cuuint64_t)(2 * cols), (cuuint64_t)rows, (cuuint64_t)n_outer};
+    cuuint64_t stride[2] = {(cuuint64_t)row_stride * sizeof(cplx), (cuuint64_t)outer_stride * sizeof(cplx)};
+    cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------ size dispatch
 #define NSB_DECL_OPS(n) extern const FftOps nsb_fft_ops_##n;
 NSB_DECL_OPS(16) NSB_DECL_OPS(32) NSB_DECL_OPS(64) NSB_DECL_OPS(128) NSB_DECL_OPS(256) NSB_DECL_OPS(512) NSB_DECL_OPS(1024)
@@ -118,6 +145,7 @@ struct nsb200_ctx {
     int system = 0, dealias = 1, kmax2 = 0, kmax = 0;
     int nzc = 0;                   // compact row stride of the workspace when kz <= kmax only is carried
     bool prune = true;             // use the dealias support windows (NSB200_NO_PRUNE=1 disables)
+    bool use_tma = true;           // TMA tile loads in the strided passes (NSB200_NO_TMA=1: cp.async path)
     bool u_in_window = false;      // resident state known to vanish outside the cube |k|_inf <= kmax
     int* flag_dev = nullptr;
     size_t field_elems = 0;        // complex elements per planar local field
@@ -288,12 +316,28 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
             for (int r = 0; r < h->nranks; ++r) a.peer_delta[r] = h->peer_delta[r];
         }
     }
+    // TMA-staged tile loads for the natural input layouts (everything on one GPU; with several ranks the y pass
+    // that reads the Fourier slab and the x pass of the contiguous-slab distribution)
+    TmaMaps maps;
+    const TmaMaps* mp = nullptr;
+    const bool natural_in = (a.in_shift == 30) && (a.in_s1 == 0);
+    if (h->use_tma && natural_in && h->ops->strided_T == 8) {
+        memset(&maps, 0, sizeof maps);
+        const long total_outer = (ps.axis == 'y') ? h->nx_loc : h->ny_loc;
+        maps.pruned = ps.in_w ? 1 : 0;
+        maps.hi_row0 = N - K;
+        for (int f = 0; f < field_cnt; ++f) {
+            CKR(encode_map(&maps.lo[f], a.src[f], ps.nzv, ps.in_w ? K + 1 : N, a.in_s2, total_outer, a.in_so, h->ops->tma_rows));
+            if (ps.in_w) CKR(encode_map(&maps.hi[f], a.src[f] + (long long)(N - K) * a.in_s2, ps.nzv, K, a.in_s2, total_outer, a.in_so, h->ops->tma_rows));
+        }
+        mp = &maps;
+    }
     {
         // minimal traffic: every carried pencil reads its non-zero inputs and writes its kept outputs once
         const double in_cnt = ps.in_w ? 2 * K + 1 : N, out_cnt = ps.out_w ? 2 * K + 1 : N;
         const double bytes = 16.0 * field_cnt * (double)n_outer * ps.nzv * (in_cnt + out_cnt);
         ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD), bytes);
-        CKI(h->ops->strided(ps.dir, &a, n_outer, field_cnt, h->stream));
+        CKI(h->ops->strided(ps.dir, &a, mp, n_outer, field_cnt, h->stream));
     }
     h->launches++;
     return 0;
@@ -591,6 +635,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     h->kmax = kmax;
     h->nzc = (kmax + 1 + 7) / 8 * 8;
     { const char* e = getenv("NSB200_NO_PRUNE"); h->prune = !(e && e[0] == '1'); }
+    { const char* e = getenv("NSB200_NO_TMA"); h->use_tma = !(e && e[0] == '1'); }
     h->ops = ops;
     h->field_elems = (size_t)h->nx_loc * h->N * h->nzp;
 #define CKC(call)                                                                                    \
@@ -607,6 +652,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     CKC(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { nsb200_destroy(h); return fail("nsb200_create: requires an sm_100a (Blackwell B200) device"); }
     h->sm_count = prop.multiProcessorCount;
+    if (h->use_tma && load_tma() != 0) { nsb200_destroy(h); return 1; }
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreate(&h->ev0));
