@@ -1,0 +1,65 @@
+"""Size-independent properties of the CUDA path at the BASELINE sizes: the optimisations must not change a bit.
+
+ * dealias-support pruning only skips loads of exact zeros and stores of modes the mask
+   zeroes, so NSB200_NO_PRUNE=1 must give a bit-identical state;
+ * the TMA tile load and the cp.async tile load feed the same butterflies (NSB200_NO_TMA=1);
+ * two ranks (slab exchange over peer memory, cyclic plane distribution) must reproduce the single-GPU step to
+   rounding (the per-pencil arithmetic is identical, so the states agree bit for bit).
+Each variant runs in its own process because the switches are read at nsb200_create time."""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CODE = r"""
+import importlib, sys, hashlib
+import numpy as np
+sys.path.insert(0, %(root)r)
+nsb = importlib.import_module("3d_navier_stokes_b200")
+n = %(n)d
+with nsb.Solver(n, nu=1e-3) as s:
+    s.initial_conditions("RANDOM_PHASE", seed=11, kp=4.0)
+    s.rk4_step(1e-3, n_steps=2)
+    u = s.get_u_hat()
+    print("HASH", hashlib.sha256(u.tobytes()).hexdigest(), "%%.17g" %% s.compute_system_measurables()[0])
+"""
+
+
+def run_variant(n, env_extra):
+    env = dict(os.environ)
+    env.update(env_extra)
+    p = subprocess.run([sys.executable, "-c", CODE % {"root": ROOT, "n": n}], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("HASH")][-1].split()
+    return line[1], float(line[2])
+
+
+@pytest.mark.parametrize("n", [64, 256, 512])
+def test_pruned_and_unpruned_paths_are_bit_identical(n):
+    h0, e0 = run_variant(n, {})
+    h1, e1 = run_variant(n, {"NSB200_NO_PRUNE": "1"})
+    assert h0 == h1 and e0 == e1
+
+
+@pytest.mark.parametrize("n", [64, 512])
+def test_tma_and_cp_async_tile_loads_are_bit_identical(n):
+    h0, _ = run_variant(n, {})
+    h1, _ = run_variant(n, {"NSB200_NO_TMA": "1"})
+    assert h0 == h1
+
+
+def test_two_ranks_match_one_rank():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "scripts", "mgpu_check.py"), "128"],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert p.stdout.count(" OK") >= 6
