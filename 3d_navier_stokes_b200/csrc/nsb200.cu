@@ -170,6 +170,11 @@ struct nsb200_ctx {
     bool p2p = false;                              // slab exchange fused into the FFT store phase over NVLink
     bool cyclic = false;                           // kx planes distributed cyclically (plane g on rank g % P) for load balance
     int* bar_dev = nullptr;
+    unsigned* flags = nullptr;                     // barrier flag page at the end of the slab (peer mapped with it)
+    unsigned epoch[NSB_BARRIER_SLOTS] = {0};
+    bool overlap = false;                          // two-stream schedule of the fused exchange (NSB200_OVERLAP=1 enables;
+                                                   // measured no gain: the link-bound kernel holds every SM slot)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     int sm_count = 0;
     int zgrid[3] = {0, 0, 0};
     long launches = 0;
@@ -206,11 +211,12 @@ static cudaEvent_t prof_event(nsb200_ctx* h) {
 }
 struct ProfScope {
     nsb200_ctx* h; cudaEvent_t a = nullptr, b = nullptr; int cls;
-    ProfScope(nsb200_ctx* h_, int cls_, double algo_bytes = 0.0) : h(h_), cls(cls_) {
-        if (h->prof_on) { a = prof_event(h); b = prof_event(h); cudaEventRecord(a, h->stream); h->prof_bytes[cls] += algo_bytes; }
+    cudaStream_t st;
+    ProfScope(nsb200_ctx* h_, int cls_, double algo_bytes = 0.0, cudaStream_t st_ = nullptr) : h(h_), cls(cls_), st(st_ ? st_ : h_->stream) {
+        if (h->prof_on) { a = prof_event(h); b = prof_event(h); cudaEventRecord(a, st); h->prof_bytes[cls] += algo_bytes; }
     }
     ~ProfScope() {
-        if (a) { cudaEventRecord(b, h->stream); h->prof.push_back({cls, a, b}); }
+        if (a) { cudaEventRecord(b, st); h->prof.push_back({cls, a, b}); }
     }
 };
 
@@ -241,7 +247,8 @@ struct PassSpec {
     bool in_w, out_w, outer_w;
     bool p2p_out = false;    // store each destination rank's block into that rank's buffer (peer memory)
 };
-static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* const* dst, int field0, int field_cnt) {
+static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* const* dst, int field0, int field_cnt, cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
     StridedArgs a;
     memset(&a, 0, sizeof a);
     for (int f = 0; f < field_cnt; ++f) { a.src[f] = src[field0 + f]; a.dst[f] = dst[field0 + f]; }
@@ -336,8 +343,8 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         // minimal traffic: every carried pencil reads its non-zero inputs and writes its kept outputs once
         const double in_cnt = ps.in_w ? 2 * K + 1 : N, out_cnt = ps.out_w ? 2 * K + 1 : N;
         const double bytes = 16.0 * field_cnt * (double)n_outer * ps.nzv * (in_cnt + out_cnt);
-        ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD), bytes);
-        CKI(h->ops->strided(ps.dir, &a, mp, n_outer, field_cnt, h->stream));
+        ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD), bytes, st);
+        CKI(h->ops->strided(ps.dir, &a, mp, n_outer, field_cnt, st));
     }
     h->launches++;
     return 0;
@@ -388,8 +395,20 @@ static int exchange(nsb200_ctx* h, cplx* const* send, cplx* const* recv, int fie
 
 // Cross-GPU barrier on the compute stream: every rank's preceding kernels (and their stores into peer memory)
 // are complete before any rank's following kernels start.
-static int gpu_barrier(nsb200_ctx* h) {
-    CKN(g_nccl.AllReduce(h->bar_dev, h->bar_dev, 1, ncclInt32, ncclSum, h->comm, h->stream));
+static PeerTable peer_table(const nsb200_ctx* h) {
+    PeerTable pt;
+    for (int r = 0; r < NSB_MAX_PEERS; ++r) pt.delta[r] = h->peer_delta[r];
+    return pt;
+}
+static int gpu_barrier(nsb200_ctx* h, cudaStream_t st = nullptr, int slot = 0) {
+    if (!st) st = h->stream;
+    if (h->p2p) {   // flag barrier over peer memory (a few microseconds)
+        k_gpu_barrier<<<1, 32, 0, st>>>(h->flags, peer_table(h), h->rank, h->nranks, slot, ++h->epoch[slot]);
+        CK(cudaGetLastError());
+        h->launches++;
+        return 0;
+    }
+    CKN(g_nccl.AllReduce(h->bar_dev, h->bar_dev, 1, ncclInt32, ncclSum, h->comm, st));
     return 0;
 }
 
@@ -415,9 +434,16 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx***
     ca.g = h->geom(in_w);
     ca.w_rs = rs;
     {
+        // with the overlapped multi-GPU schedule the curl runs on the second stream, beside the y pass of u
+        cudaStream_t cs = (h->p2p && h->overlap) ? h->comm_stream : h->stream;
+        if (cs != h->stream) {
+            CK(cudaEventRecord(h->ev_c, h->stream));       // `in` and the workspace are ready
+            CK(cudaStreamWaitEvent(cs, h->ev_c, 0));
+        }
         const double kw = in_w ? 2.0 * h->kmax + 1 : h->N;   // kx planes are counted globally / nranks (slab average)
-        ProfScope ps(h, NSB200_PC_CURL, 16.0 * 6.0 * (kw * kw / h->nranks) * nz_in);
-        k_curl<<<rg, nsb200_ctx::row_block(nz_in), 0, h->stream>>>(ca);
+        ProfScope ps(h, NSB200_PC_CURL, 16.0 * 6.0 * (kw * kw / h->nranks) * nz_in, cs);
+        k_curl<<<rg, nsb200_ctx::row_block(nz_in), 0, cs>>>(ca);
+        if (cs != h->stream) CK(cudaEventRecord(h->ev_fork, cs));
     }
     CK(cudaGetLastError());
     h->launches++;
@@ -445,6 +471,40 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx***
         cplx* srcp[6] = {in[0], in[1], in[2], h->W[0], h->W[1], h->W[2]};
         yinv_u.p2p_out = yinv_w.p2p_out = true;
         xfwd.p2p_out = true;
+        if (h->overlap) {
+            // Two streams: while one field group drains over NVLink (store phase of the y / forward-x pass), the
+            // other group's HBM-bound local pass runs.  S1 did the curl (launched above on S0? no: see below).
+            cudaStream_t S0 = h->stream, S1 = h->comm_stream;
+            CKR(run_pass(h, yinv_u, srcp, h->R, 0, 3, S0));            // u: needs no curl
+            CK(cudaEventRecord(h->ev_a, S0));
+            CK(cudaStreamWaitEvent(S1, h->ev_fork, 0));                // curl (recorded by the caller section below)
+            CK(cudaStreamWaitEvent(S1, h->ev_a, 0));                   // one group on the links at a time
+            CKR(run_pass(h, yinv_w, srcp, h->R, 3, 3, S1));
+            CKR(gpu_barrier(h, S1, 1));
+            CKR(run_pass(h, xinv, h->R, h->R, 3, 3, S1));
+            CK(cudaEventRecord(h->ev_b, S1));
+            CKR(gpu_barrier(h, S0, 0));
+            CKR(run_pass(h, xinv, h->R, h->R, 0, 3, S0));
+            CK(cudaStreamWaitEvent(S0, h->ev_b, 0));
+            CKR(run_z(h, NSB_Z_FUSED, 3, h->R, rs, nz_in, nz_out));
+            // forward: push component f while the y pass of component f-1 runs
+            CKR(run_pass(h, xfwd, h->R, h->W + 3, 0, 1, S0));
+            CK(cudaEventRecord(h->ev_a, S0));
+            CKR(run_pass(h, xfwd, h->R, h->W + 3, 1, 1, S0));
+            CK(cudaEventRecord(h->ev_b, S0));
+            CKR(run_pass(h, xfwd, h->R, h->W + 3, 2, 1, S0));
+            CK(cudaStreamWaitEvent(S1, h->ev_a, 0));
+            CKR(gpu_barrier(h, S1, 2));
+            CKR(run_pass(h, yfwd, h->W + 3, h->W, 0, 1, S1));
+            CK(cudaStreamWaitEvent(S1, h->ev_b, 0));
+            CKR(gpu_barrier(h, S1, 3));
+            CKR(run_pass(h, yfwd, h->W + 3, h->W, 1, 1, S1));
+            CK(cudaEventRecord(h->ev_join, S1));
+            CKR(gpu_barrier(h, S0, 4));
+            CKR(run_pass(h, yfwd, h->W + 3, h->W, 2, 1, S0));
+            CK(cudaStreamWaitEvent(S0, h->ev_join, 0));
+            return 0;   // result in W[0..2]
+        }
         CKR(run_pass(h, yinv_u, srcp, h->R, 0, 3));
         CKR(run_pass(h, yinv_w, srcp, h->R, 3, 3));
         CKR(gpu_barrier(h));
@@ -601,6 +661,7 @@ int nsb200_destroy(nsb200_ctx* h) {
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     for (auto e : h->ev_field) cudaEventDestroy(e);
     for (auto e : h->ev_comm) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_fork, h->ev_join, h->ev_a, h->ev_b, h->ev_c}) if (e) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -657,14 +718,21 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     CKC(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreate(&h->ev0));
     CKC(cudaEventCreate(&h->ev1));
+    CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_c, cudaEventDisableTiming));
+    { const char* e = getenv("NSB200_OVERLAP"); h->overlap = (e && e[0] == '1'); }
     for (int i = 0; i < 6; ++i) {
         cudaEvent_t e;
         CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_field.push_back(e);
         CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_comm.push_back(e);
     }
     const int nfields = (n_ranks > 1) ? 21 : 15;
-    h->bytes = (size_t)nfields * h->field_elems * sizeof(cplx);
+    h->bytes = (size_t)nfields * h->field_elems * sizeof(cplx) + 4096;   // + barrier flag page
     CKC(cudaMalloc(&h->slab, h->bytes));
+    h->flags = reinterpret_cast<unsigned*>(h->slab + (size_t)nfields * h->field_elems);
     CKC(cudaMemsetAsync(h->slab, 0, h->bytes, h->stream));
     for (int d = 0; d < 3; ++d) {
         h->U[d] = h->slab + (size_t)d * h->field_elems;
@@ -762,11 +830,6 @@ long nsb200_local_fourier_elems(nsb200_ctx* h) { return h ? 3L * h->nx_loc * h->
 long nsb200_launch_count(nsb200_ctx* h) { return h ? h->launches : 0; }
 long nsb200_device_bytes(nsb200_ctx* h) { return h ? (long)h->bytes : 0; }
 
-static PeerTable peer_table(const nsb200_ctx* h) {
-    PeerTable pt;
-    for (int r = 0; r < NSB_MAX_PEERS; ++r) pt.delta[r] = h->peer_delta[r];
-    return pt;
-}
 static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
     const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
     cplx* stage = h->W[0];   // W is one contiguous 6-field buffer >= the 3-field host layout
@@ -1031,6 +1094,7 @@ int nsb200_profile_read(nsb200_ctx* h, double ms[NSB200_PC_COUNT], long counts[N
     if (!h || !ms || !counts) return fail("nsb200_profile_read: null argument");
     CKR(set_device(h));
     CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->comm_stream));
     for (int i = 0; i < NSB200_PC_COUNT; ++i) { ms[i] = 0.0; counts[i] = 0; }
     for (auto& r : h->prof) {
         float t = 0.f;

@@ -106,6 +106,28 @@ __global__ void k_planar_to_aos_gather(cplx* __restrict__ aos, const cplx* p0, c
     }
 }
 
+// Cross-GPU barrier over peer memory: every rank writes its epoch into slot[rank] of every peer's flag page and
+// waits until all peers' epochs have arrived in its own page.  Kernel boundaries order it against the FFT kernels
+// whose peer stores it publishes; bounded spin so that a lost peer traps instead of hanging the GPU.
+#define NSB_BARRIER_SLOTS 8
+__global__ void k_gpu_barrier(unsigned* flags, PeerTable pt, int rank, int nranks, int slot, unsigned epoch) {
+    __shared__ long long s_delta[NSB_MAX_PEERS];
+    if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = pt.delta[threadIdx.x];
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        __threadfence_system();
+        volatile unsigned* peer = reinterpret_cast<volatile unsigned*>(reinterpret_cast<char*>(flags) + s_delta[r]) + slot * NSB_MAX_PEERS + rank;
+        *peer = epoch;
+        volatile unsigned* mine = reinterpret_cast<volatile unsigned*>(flags) + slot * NSB_MAX_PEERS + r;
+        unsigned spin = 0;
+        while ((int)(*mine - epoch) < 0) {
+            if (++spin > (1u << 25)) __trap();
+        }
+        __threadfence_system();
+    }
+}
+
 // real fields: host [x][y][Nz+2][3] doubles (solver.c:667-672) <-> planar rows of 2*nzp doubles
 __global__ void k_real_aos_to_planar(const double* __restrict__ aos, double* p0, double* p1, double* p2, Geom g, long long nrows) {
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
