@@ -32,6 +32,8 @@ SYMBOLS = [
     ("nsb200_spectra", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     ("nsb200_fft_r2c", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     ("nsb200_fft_c2r", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    ("nsb200_download_what", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    ("nsb200_download_real", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     ("nsb200_initial_condition", ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_ulonglong, ctypes.c_double, ctypes.c_double]),
     ("nsb200_host_register", ctypes.c_int, [ctypes.c_void_p, ctypes.c_ulonglong]),
     ("nsb200_host_unregister", ctypes.c_int, [ctypes.c_void_p]),

@@ -993,11 +993,51 @@ int nsb200_fft_c2r(nsb200_ctx* h, const double* cplx_in, double* real_out) {
     h->launches++;
     CKR(fft3_c2r_inplace(h));
     double* stage = reinterpret_cast<double*>(h->W[3]);
-    k_real_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, (double*)h->W[0], (double*)h->W[1], (double*)h->W[2], h->geom(), h->nrows());
+    k_real_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, (double*)h->W[0], (double*)h->W[1], (double*)h->W[2], h->geom(), h->nrows(), 1.0);
     CK(cudaGetLastError());
     h->launches++;
     const size_t nreal = (size_t)3 * h->N * h->N * (h->N + 2);
     CK(cudaMemcpyAsync(real_out, stage, nreal * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// w_hat = i k x u_hat of the resident state into ACC (scratch between steps), full spectrum
+static int curl_of_state(nsb200_ctx* h) {
+    CurlArgs ca;
+    for (int d = 0; d < 3; ++d) { ca.u[d] = h->U[d]; ca.w[d] = h->ACC[d]; }
+    ca.g = h->geom(false);
+    ca.w_rs = h->nzp;
+    k_curl<<<h->row_grid(), nsb200_ctx::row_block(h->nzf), 0, h->stream>>>(ca);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int nsb200_download_what(nsb200_ctx* h, double* w_hat_host) {
+    if (!h || !w_hat_host) return fail("nsb200_download_what: null argument");
+    CKR(set_device(h));
+    CKR(curl_of_state(h));
+    return download_from(h, w_hat_host, h->ACC);
+}
+
+int nsb200_download_real(nsb200_ctx* h, int which, double* real_host) {
+    if (!h || !real_host) return fail("nsb200_download_real: null argument");
+    if (which != 0 && which != 1) return fail("nsb200_download_real: which must be 0 (u) or 1 (w)");
+    if (h->nranks != 1) return fail("nsb200_download_real: single rank only");
+    CKR(set_device(h));
+    cplx* const* src = h->U;
+    if (which == 1) { CKR(curl_of_state(h)); src = h->ACC; }
+    for (int d = 0; d < 3; ++d)
+        CK(cudaMemcpyAsync(h->W[d], src[d], h->field_elems * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
+    CKR(fft3_c2r_inplace(h));                                       // hdf5_funcs.c:588 / :665
+    double* stage = reinterpret_cast<double*>(h->W[3]);
+    const double n3 = (double)h->N * (double)h->N * (double)h->N;
+    k_real_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, (double*)h->W[0], (double*)h->W[1], (double*)h->W[2], h->geom(), h->nrows(), 1.0 / n3);
+    CK(cudaGetLastError());
+    h->launches++;
+    const size_t nreal = (size_t)3 * h->N * h->N * (h->N + 2);
+    CK(cudaMemcpyAsync(real_host, stage, nreal * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }

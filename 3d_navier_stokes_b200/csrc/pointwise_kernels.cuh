@@ -139,14 +139,14 @@ __global__ void k_real_aos_to_planar(const double* __restrict__ aos, double* p0,
         }
     }
 }
-__global__ void k_real_planar_to_aos(double* __restrict__ aos, const double* p0, const double* p1, const double* p2, Geom g, long long nrows) {
+__global__ void k_real_planar_to_aos(double* __restrict__ aos, const double* p0, const double* p1, const double* p2, Geom g, long long nrows, double scale) {
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         double* dst = aos + row * (g.N + 2) * 3;
         for (int k = threadIdx.x; k < g.N + 2; k += blockDim.x) {
             const bool in = k < g.N;
-            dst[3 * k + 0] = in ? p0[row * 2 * g.nzp + k] : 0.0;
-            dst[3 * k + 1] = in ? p1[row * 2 * g.nzp + k] : 0.0;
-            dst[3 * k + 2] = in ? p2[row * 2 * g.nzp + k] : 0.0;
+            dst[3 * k + 0] = in ? p0[row * 2 * g.nzp + k] * scale : 0.0;
+            dst[3 * k + 1] = in ? p1[row * 2 * g.nzp + k] * scale : 0.0;
+            dst[3 * k + 2] = in ? p2[row * 2 * g.nzp + k] * scale : 0.0;
         }
     }
 }

@@ -82,6 +82,18 @@ class Solver:
         self.lib.check(self.lib.nsb200_download_uhat(self.h, out.ctypes.data), "nsb200_download_uhat")
         return out
 
+    def get_w_hat(self):
+        """run_data->w_hat = i k x u_hat (never computed by the reference)."""
+        out = np.empty(self.shape_f, dtype=np.complex128)
+        self.lib.check(self.lib.nsb200_download_what(self.h, out.ctypes.data), "nsb200_download_what")
+        return out
+
+    def get_real(self, which="u"):
+        """Real-space u or w as the reference's save path dumps them (hdf5_funcs.c:588-602): [Nx][Ny][Nz+2][3], scaled 1/N^3."""
+        out = np.empty(self.shape_r, dtype=np.float64)
+        self.lib.check(self.lib.nsb200_download_real(self.h, 0 if which == "u" else 1, out.ctypes.data), "nsb200_download_real")
+        return out
+
     def upload_ptr(self, ptr):
         self.lib.check(self.lib.nsb200_upload_uhat(self.h, ptr), "nsb200_upload_uhat")
 

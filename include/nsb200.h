@@ -122,6 +122,14 @@ int nsb200_spectra(nsb200_ctx* h, double* enrg_spect, double* enst_spect, int n_
 int nsb200_fft_r2c(nsb200_ctx* h, const double* real_in, double* cplx_out);
 int nsb200_fft_c2r(nsb200_ctx* h, const double* cplx_in, double* real_out);
 
+/* Dataset helpers for the save path (cold): run_data->w_hat = i k x u_hat of the resident state (allocated,
+ * zero-filled and written by the reference, hdf5_funcs.c:186,639, but never computed - SURVEY Q13), and the
+ * real-space fields u (which = 0) / w (which = 1) as WriteDataToFile produces them under __REALSPACE /
+ * __VORT_REAL: non-transposed batch c2r and 1/(NxNyNz) scaling (hdf5_funcs.c:588-602, 665-679), layout
+ * [Nx][Ny][Nz+2][3].  nsb200_download_real is single rank only. */
+int nsb200_download_what(nsb200_ctx* h, double* w_hat_host);
+int nsb200_download_real(nsb200_ctx* h, int which, double* real_host);
+
 /* Replaces InitialConditions (solver.c:1537-1648, fixes F3/F5) on the device: "TAYLOR_GREEN",
  * "SHAPIRO" (real-space fill, batch r2c, dealias) or "RANDOM_PHASE" (the partition-independent
  * synthetic field of SURVEY 8d: seed, peak wavenumber kp, rescaled to `energy`). */

@@ -218,6 +218,23 @@ def test_spectra_vs_oracle():
     assert e.sum() == pytest.approx(o.measurables(u, N, 0.0)["energy"], rel=1e-12)
 
 
+def test_vorticity_and_real_space_dumps():
+    """w_hat (Q13) and the normalised real-space fields of the save path (hdf5_funcs.c:588-602)."""
+    n = 32; N = (n, n, n)
+    u = o.random_phase_ic(N, seed=21, kp=4.0)
+    with nsb.Solver(n) as s:
+        s.set_u_hat(u)
+        w_hat = s.get_w_hat()
+        ur = s.get_real("u")
+        wr = s.get_real("w")
+        assert np.array_equal(s.get_u_hat(), u)          # the state is not disturbed
+    w_ref = o.curl_hat(u, N)
+    assert np.array_equal(w_hat, w_ref)                   # pointwise, explicitly rounded: bit exact
+    assert np.abs(ur[:, :, :n, :] - o.c2r(u, N) / n ** 3).max() < 1e-14 * np.abs(ur).max()
+    assert np.abs(wr[:, :, :n, :] - o.c2r(w_ref, N) / n ** 3).max() < 1e-14 * np.abs(wr).max()
+    assert np.all(ur[:, :, n:, :] == 0)
+
+
 # ----------------------------------------------------------------------------- golden vectors from the reference's own C
 @pytest.mark.parametrize("tag", ["ref_rp16", "ref_rp32", "ref_tg32", "ref_rp16_hyper"])
 def test_golden_one_step_maps(tag):
