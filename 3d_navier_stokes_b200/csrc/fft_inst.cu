@@ -17,8 +17,10 @@ constexpr size_t kStridedSmem = (size_t)BP::NPAD * ST * sizeof(cplx);
 constexpr size_t kZSmem = (size_t)ZP::NPAD * ZCfg<ZP>::G * sizeof(cplx);
 constexpr size_t kZFusedSmem = (size_t)6 * ZF::NPAD * ZFusedCfg<ZF>::G * sizeof(cplx);
 
+int pipe_setup();
 int setup() {
     cudaError_t e;
+    { int pe = pipe_setup(); if (pe != 0) return pe; }
     e = cudaFuncSetAttribute(k_fft_strided<BP, ST, STP, FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fft_strided<BP, ST, STP, INV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStridedSmem);
@@ -49,6 +51,46 @@ int strided(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff,
     return (int)cudaGetLastError();
 }
 
+#if NSB_N == 512
+#ifndef NSB_PIPE_T
+#define NSB_PIPE_T 8
+#endif
+constexpr int PT = NSB_PIPE_T;
+constexpr size_t kPipeSmem = (size_t)2 * NSB_N * PT * sizeof(cplx);
+int strided_pipe(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s) {
+    PipeArgs pa;
+    pa.nzt = (a->nzv + PT - 1) / PT;
+    pa.n_outer_eff = n_outer_eff;
+    pa.total_tiles = pa.nzt * n_outer_eff * nfields;
+    if (pa.total_tiles == 0) return 0;
+    int grid = pa.total_tiles < max_ctas ? pa.total_tiles : max_ctas;
+    pa.tiles_per_cta = (pa.total_tiles + grid - 1) / grid;
+    grid = (pa.total_tiles + pa.tiles_per_cta - 1) / pa.tiles_per_cta;
+    if (dir == FWD) k_fft_strided_pipe<BP, FWD, PT><<<grid, PT * BP::NB1, kPipeSmem, s>>>(*a, *maps, pa);
+    else k_fft_strided_pipe<BP, INV, PT><<<grid, PT * BP::NB1, kPipeSmem, s>>>(*a, *maps, pa);
+    return (int)cudaGetLastError();
+}
+int pipe_setup() {
+    cudaError_t e = cudaFuncSetAttribute(k_fft_strided_pipe<BP, FWD, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fft_strided_pipe<BP, INV, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem);
+    return (int)e;
+}
+int pipe_occupancy() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fft_strided_pipe<BP, INV, PT>, PT * BP::NB1, kPipeSmem);
+    return n;
+}
+#define NSB_PIPE_FN strided_pipe
+#define NSB_PIPE_TCOLS PT
+#define NSB_PIPE_OCC pipe_occupancy
+#else
+int pipe_setup() { return 0; }
+#define NSB_PIPE_FN nullptr
+#define NSB_PIPE_TCOLS 0
+#define NSB_PIPE_OCC nullptr
+#endif
+
 int zlaunch(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s) {
     if (a->npairs == 0) return 0;
     constexpr int TH = ZCfg<ZP>::THREADS;
@@ -68,4 +110,4 @@ int zocc(int which) {
 }
 }  // namespace
 
-extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G}, setup, strided, zlaunch, zocc};
+extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, NSB_PIPE_TCOLS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC};

@@ -210,6 +210,95 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a, con
     }
 }
 
+// Persistent, double-buffered variant of the strided pass (natural input layouts, TMA): a CTA walks a
+// contiguous run of tiles; while it transforms tile i in one shared-memory buffer, the TMA boxes of tile i+1 are
+// already in flight into the other, so the SM always has a tile outstanding in HBM.  T = 4 kz columns per tile
+// (2 x N*64 B of shared memory per CTA keeps three CTAs resident at N = 512).
+struct PipeArgs {
+    int nzt;            // kz tiles per (outer, field)
+    int n_outer_eff;    // outer indices actually processed
+    int total_tiles;    // nzt * n_outer_eff * nfields
+    int tiles_per_cta;
+};
+template <class P, int DIR, int T>
+__global__ void __launch_bounds__(T * P::NB1, (T == 4) ? 3 : 1) k_fft_strided_pipe(const StridedArgs a, const __grid_constant__ TmaMaps maps, const PipeArgs pa) {
+    constexpr int TP = P::NB1, N = P::N;
+    static_assert(P::ROW == P::M1, "pipelined strided pass needs an unpadded plan");
+    extern __shared__ __align__(1024) unsigned char nsb_smem_raw[];
+    cplx* smem = reinterpret_cast<cplx*>(nsb_smem_raw);
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ long long s_delta[NSB_MAX_PEERS];
+    if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = a.peer_delta[threadIdx.x];
+    const int p = threadIdx.x % T, q = threadIdx.x / T;
+    const cplx* __restrict__ tw = a.tw;
+#ifdef __CUDA_ARCH__
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) { nsb_mbar_init(bar0, 1); nsb_mbar_init(bar0 + 8, 1); }
+    __syncthreads();
+    const int t0 = blockIdx.x * pa.tiles_per_cta;
+    const int t1 = (t0 + pa.tiles_per_cta < pa.total_tiles) ? t0 + pa.tiles_per_cta : pa.total_tiles;
+    auto issue = [&](int t, int buf) {
+        const int kzt = t % pa.nzt, rest = t / pa.nzt;
+        int outer = rest % pa.n_outer_eff;
+        const int field = rest / pa.n_outer_eff;
+        if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
+        constexpr int ROWS = TmaChunk<N>::ROWS, COUNT = TmaChunk<N>::COUNT;
+        const unsigned bar = bar0 + 8u * buf;
+        nsb_mbar_expect_tx(bar, (unsigned)(N * T * sizeof(cplx)));
+#pragma unroll
+        for (int c = 0; c < COUNT; ++c) {
+            const bool use_hi = maps.pruned && (c >= COUNT / 2);
+            const void* mp = use_hi ? (const void*)&maps.hi[field] : (const void*)&maps.lo[field];
+            const int row = use_hi ? c * ROWS - maps.hi_row0 : c * ROWS;
+            nsb_tma_load_3d(sbase + (unsigned)((buf * N + c * ROWS) * T * sizeof(cplx)), mp, kzt * T * 2, row, outer, bar);
+        }
+    };
+    if (threadIdx.x == 0 && t0 < t1) issue(t0, 0);
+    const long long os1 = a.out_s1, os2 = a.out_s2;
+    const int osh = a.out_shift, omk = a.out_mask, slo = a.out_skip_lo, shi = a.out_skip_hi;
+    for (int t = t0; t < t1; ++t) {
+        const int it = t - t0, buf = it & 1;
+        if (threadIdx.x == 0 && t + 1 < t1) issue(t + 1, buf ^ 1);   // that buffer was released by the barrier ending the previous trip
+        const int kzt = t % pa.nzt, rest = t / pa.nzt;
+        int outer = rest % pa.n_outer_eff;
+        const int field = rest / pa.n_outer_eff;
+        if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
+        const int kz = kzt * T + p;
+        const bool valid = kz < a.nzv;
+        cplx* dst = a.dst[field] + ((long long)outer * a.out_so + kz);
+        cplx* sm = smem + (size_t)buf * N * T + p;
+        nsb_mbar_wait(bar0 + 8u * buf, (unsigned)((it >> 1) & 1));
+        for (int b = q; b < P::NB1; b += TP) fft_pass1_inplace<P, DIR, T>(b, sm, tw);
+        __syncthreads();
+        if constexpr (P::PASSES == 3) {
+            for (int b = q; b < P::NB2; b += TP) fft_pass2<P, DIR, T>(b, sm, tw);
+            __syncthreads();
+        }
+        for (int b = q; b < P::NBL; b += TP) {
+            cplx v[P::RL];
+            fft_pass_last<P, DIR, T>(b, sm, v);
+            if (valid) {
+#pragma unroll
+                for (int k2 = 0; k2 < P::RL; ++k2) {
+                    const int n = b + k2 * P::NBL;
+                    if (!(n >= slo && n < shi)) {
+                        if (a.out_p2p) {
+                            const int hi = n >> osh, lo = n & omk;
+                            cplx* d = reinterpret_cast<cplx*>(reinterpret_cast<char*>(dst) + s_delta[a.out_rank_lo ? lo : hi]);
+                            d[(long long)(a.out_rank_lo ? hi : lo) * os2] = v[k2];
+                        } else {
+                            dst[(long long)(n >> osh) * os1 + (long long)(n & omk) * os2] = v[k2];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // every read of this buffer is done: it may be refilled
+    }
+#endif
+}
+
 // ------------------------------------------------------------------------------ z pencils
 struct ZArgs {
     cplx* base;                // field f starts at base + f * fstride; rows of `rs` complex (= 2*rs doubles when real)
@@ -467,4 +556,4 @@ template <> struct StridedCfg<64> { static constexpr int T = 8, TP = 8; };
 template <> struct StridedCfg<128> { static constexpr int T = 8, TP = 8; };
 template <> struct StridedCfg<256> { static constexpr int T = 8, TP = 16; };
 template <> struct StridedCfg<512> { static constexpr int T = 8, TP = 32; };
-template <> struct StridedCfg<1024> { static constexpr int T = 4, TP = 64; };
+template <> struct StridedCfg<1024> { static constexpr int T = 8, TP = 64; };   // 128-byte segments (T = 4 halved the DRAM efficiency)

@@ -9,6 +9,7 @@ struct FftOps {
     int N;
     int strided_T;                 // kz columns per strided tile
     int tma_rows;                  // rows per TMA box of the strided tile load
+    int pipe_T;                    // kz columns per tile of the persistent strided pass (0: not built)
     int z_pairs_per_cta[3];        // row pairs per CTA for NSB_Z_C2R / _R2C / _FUSED
     int (*setup)(void);            // opt-in to large dynamic shared memory; returns cudaError_t
     // one c2c pass over `nfields` fields; grid = (ceil(nzv/T), n_outer_eff, nfields)
@@ -18,6 +19,9 @@ struct FftOps {
     int (*z)(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s);
     // resident CTAs per SM of a z kernel (for sizing the persistent grid)
     int (*z_occupancy)(int which);
+    // persistent double-buffered strided pass (T = 4, TMA, natural input layout); NULL when not built for this N
+    int (*strided_pipe)(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s);
+    int (*pipe_occupancy)(void);
 };
 
 const FftOps* nsb_get_fft_ops(int N);

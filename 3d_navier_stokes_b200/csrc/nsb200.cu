@@ -109,10 +109,10 @@ static int load_tma() {
 }
 // rank-3 FP64 view of a pencil family: dim0 = 2*cols doubles (contiguous), dim1 = rows (row_stride complex apart),
 // dim2 = outer (outer_stride complex apart); box = [16 doubles][box_rows][1]
-static int encode_map(CUtensorMap* m, const cplx* base, long cols, long rows, long row_stride, long n_outer, long outer_stride, int box_rows) {
+static int encode_map(CUtensorMap* m, const cplx* base, long cols, long rows, long row_stride, long n_outer, long outer_stride, int box_rows, int box_cols = 8) {
     cuuint64_t dim[3] = {(cuuint64_t)(2 * cols), (cuuint64_t)rows, (cuuint64_t)n_outer};
     cuuint64_t stride[2] = {(cuuint64_t)row_stride * sizeof(cplx), (cuuint64_t)outer_stride * sizeof(cplx)};
-    cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)(2 * box_cols), (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -146,6 +146,8 @@ struct nsb200_ctx {
     int nzc = 0;                   // compact row stride of the workspace when kz <= kmax only is carried
     bool prune = true;             // use the dealias support windows (NSB200_NO_PRUNE=1 disables)
     bool use_tma = true;           // TMA tile loads in the strided passes (NSB200_NO_TMA=1: cp.async path)
+    bool use_pipe = false;         // persistent double-buffered strided pass where built (NSB200_PIPE=1 enables; measured equal)
+    int pipe_ctas = 0;
     bool u_in_window = false;      // resident state known to vanish outside the cube |k|_inf <= kmax
     int* flag_dev = nullptr;
     size_t field_elems = 0;        // complex elements per planar local field
@@ -188,10 +190,21 @@ struct nsb200_ctx {
     Geom geom(bool windowed = false) const {
         Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.kcut = windowed ? kmax : N;
         g.x_start = cyclic ? rank : x_start; g.x_stride = cyclic ? nranks : 1;
+        g.pl_lo = g.pl_hi = 0;
+        if (windowed) plane_window(g.pl_lo, g.pl_hi);
         return g;
     }
+    // local planes whose global index lies in (kmax, N - kmax): [lo, hi)
+    void plane_window(int& lo, int& hi) const {
+        const int x0 = cyclic ? rank : x_start, xs = cyclic ? nranks : 1, K = kmax;
+        lo = (K - x0 >= 0) ? (K - x0) / xs + 1 : 0;
+        hi = (N - K - x0 > 0) ? (N - K - x0 + xs - 1) / xs : 0;
+        lo = lo < 0 ? 0 : (lo > nx_loc ? nx_loc : lo);
+        hi = hi < 0 ? 0 : (hi > nx_loc ? nx_loc : hi);
+        if (hi < lo) hi = lo;
+    }
     // the boundary's contiguous slab (fftw_mpi_local_size_many)
-    Geom geom_api() const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.kcut = N; g.x_start = x_start; g.x_stride = 1; return g; }
+    Geom geom_api() const { Geom g; g.N = N; g.nzf = nzf; g.nzp = nzp; g.nx_loc = nx_loc; g.kcut = N; g.x_start = x_start; g.x_stride = 1; g.pl_lo = g.pl_hi = 0; return g; }
     long long nrows() const { return (long long)nx_loc * N; }
     int row_grid() const { long long r = nrows(); long long cap = (long long)sm_count * 32; return (int)(r < cap ? r : cap); }
     // threads per CTA for row kernels that walk nk modes of a row: one trip per row, few idle lanes
@@ -264,8 +277,8 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         n_outer = h->nx_loc;
         if (ps.outer_w) {   // local kx planes with global index in [K+1, N-K) carry nothing
             // global index of local plane i: x0 + i*xs ; first i above K, first i at or above N-K
-            const int x0 = h->cyclic ? h->rank : h->x_start, xs = h->cyclic ? h->nranks : 1;
-            int lo = (K - x0 >= 0) ? (K - x0) / xs + 1 : 0, hi = (N - K - x0 > 0) ? (N - K - x0 + xs - 1) / xs : 0;
+            int lo, hi;
+            h->plane_window(lo, hi);
             lo = lo < 0 ? 0 : (lo > h->nx_loc ? h->nx_loc : lo);
             hi = hi < 0 ? 0 : (hi > h->nx_loc ? h->nx_loc : hi);
             if (hi > lo) { a.outer_lo = lo; a.outer_hi = hi; n_outer -= hi - lo; }
@@ -328,14 +341,16 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
     TmaMaps maps;
     const TmaMaps* mp = nullptr;
     const bool natural_in = (a.in_shift == 30) && (a.in_s1 == 0);
-    if (h->use_tma && natural_in && h->ops->strided_T == 8) {
+    const bool pipe = h->use_pipe && h->use_tma && natural_in && h->ops->strided_pipe != nullptr;
+    if (h->use_tma && natural_in && (h->ops->strided_T == 8 || pipe)) {
         memset(&maps, 0, sizeof maps);
+        const int bc = pipe ? h->ops->pipe_T : 8;
         const long total_outer = (ps.axis == 'y') ? h->nx_loc : h->ny_loc;
         maps.pruned = ps.in_w ? 1 : 0;
         maps.hi_row0 = N - K;
         for (int f = 0; f < field_cnt; ++f) {
-            CKR(encode_map(&maps.lo[f], a.src[f], ps.nzv, ps.in_w ? K + 1 : N, a.in_s2, total_outer, a.in_so, h->ops->tma_rows));
-            if (ps.in_w) CKR(encode_map(&maps.hi[f], a.src[f] + (long long)(N - K) * a.in_s2, ps.nzv, K, a.in_s2, total_outer, a.in_so, h->ops->tma_rows));
+            CKR(encode_map(&maps.lo[f], a.src[f], ps.nzv, ps.in_w ? K + 1 : N, a.in_s2, total_outer, a.in_so, h->ops->tma_rows, bc));
+            if (ps.in_w) CKR(encode_map(&maps.hi[f], a.src[f] + (long long)(N - K) * a.in_s2, ps.nzv, K, a.in_s2, total_outer, a.in_so, h->ops->tma_rows, bc));
         }
         mp = &maps;
     }
@@ -344,7 +359,8 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         const double in_cnt = ps.in_w ? 2 * K + 1 : N, out_cnt = ps.out_w ? 2 * K + 1 : N;
         const double bytes = 16.0 * field_cnt * (double)n_outer * ps.nzv * (in_cnt + out_cnt);
         ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD), bytes, st);
-        CKI(h->ops->strided(ps.dir, &a, mp, n_outer, field_cnt, st));
+        if (pipe) CKI(h->ops->strided_pipe(ps.dir, &a, mp, n_outer, field_cnt, h->pipe_ctas, st));
+        else CKI(h->ops->strided(ps.dir, &a, mp, n_outer, field_cnt, st));
     }
     h->launches++;
     return 0;
@@ -697,6 +713,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     h->nzc = (kmax + 1 + 7) / 8 * 8;
     { const char* e = getenv("NSB200_NO_PRUNE"); h->prune = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_NO_TMA"); h->use_tma = !(e && e[0] == '1'); }
+    { const char* e = getenv("NSB200_PIPE"); h->use_pipe = (e && e[0] == '1'); }
     h->ops = ops;
     h->field_elems = (size_t)h->nx_loc * h->N * h->nzp;
 #define CKC(call)                                                                                    \
@@ -764,6 +781,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     {
         int e = ops->setup();
         if (e != 0) { fail(std::string("kernel attribute setup failed: ") + cudaGetErrorString((cudaError_t)e)); nsb200_destroy(h); return 1; }
+        if (ops->pipe_occupancy) { int occ = ops->pipe_occupancy(); h->pipe_ctas = (occ > 0 ? occ : 1) * h->sm_count; }
         for (int w = 0; w < 3; ++w) {
             int occ = ops->z_occupancy(w);
             if (occ < 1) { fail("z kernel does not fit on an SM"); nsb200_destroy(h); return 1; }

@@ -16,7 +16,24 @@ struct Geom {
     int x_start;  // global index of the first local kx plane
     int x_stride; // global index distance between consecutive local planes (1: contiguous slab; P: cyclic)
     int kcut;     // support window: only |kx|, |ky| <= kcut and kz <= kcut are touched (kcut >= N: everything)
+    int pl_lo;    // local planes [pl_lo, pl_hi) lie outside the window (empty range when not windowed)
+    int pl_hi;
 };
+
+// Row walk of the in-step pointwise kernels.  Compact index over the rows inside the support window only
+// (no skipped trips), dealt to CTAs in chunks of NSB_ROWS_PER_CTA consecutive rows so that each of the
+// ~15 array streams is touched in long contiguous runs.
+#define NSB_ROWS_PER_CTA 4
+NSB_HD long long nsb_window_rows(const Geom& g) {
+    const int nj = (g.kcut < g.N) ? 2 * g.kcut + 1 : g.N;
+    return (long long)(g.nx_loc - (g.pl_hi - g.pl_lo)) * nj;
+}
+NSB_HD void nsb_window_row(const Geom& g, long long rc, int& i, int& j) {
+    const int nj = (g.kcut < g.N) ? 2 * g.kcut + 1 : g.N;
+    const int ic = (int)(rc / nj), jc = (int)(rc % nj);
+    i = ic < g.pl_lo ? ic : ic + (g.pl_hi - g.pl_lo);
+    j = (g.kcut < g.N && jc > g.kcut) ? jc + (g.N - nj) : jc;
+}
 
 NSB_HD bool nsb_in_window(int kx, int ky, int kcut) { return kx <= kcut && -kx <= kcut && ky <= kcut && -ky <= kcut; }
 NSB_HD int nsb_kz_count(const Geom& g) { return g.kcut + 1 < g.nzf ? g.kcut + 1 : g.nzf; }
@@ -160,11 +177,13 @@ struct CurlArgs {
 };
 __global__ void k_curl(const CurlArgs a) {
     const Geom g = a.g;
-    const long long nrows = (long long)g.nx_loc * g.N;
-    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const int i = (int)(row / g.N), j = (int)(row % g.N);
+    const long long nrc = nsb_window_rows(g);
+    for (long long rc0 = (long long)blockIdx.x * NSB_ROWS_PER_CTA; rc0 < nrc; rc0 += (long long)gridDim.x * NSB_ROWS_PER_CTA)
+    for (long long rc = rc0; rc < rc0 + NSB_ROWS_PER_CTA && rc < nrc; ++rc) {
+        int i, j;
+        nsb_window_row(g, rc, i, j);
+        const long long row = (long long)i * g.N + j;
         const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
-        if (!nsb_in_window(kx, ky, g.kcut)) continue;
         const long long base = row * g.nzp, wbase = row * a.w_rs;
         const int nk = nsb_kz_count(g);
         for (int k = threadIdx.x; k < nk; k += blockDim.x) {
@@ -221,13 +240,18 @@ NSB_HD void project_mode(int kx, int ky, int kz, double norm, int dealias, int k
 
 __global__ void k_rk_stage(const RkArgs a) {
     const Geom g = a.g;
-    const long long nrows = (long long)g.nx_loc * g.N;
-    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const int i = (int)(row / g.N), j = (int)(row % g.N);
+    // skip_outside: walk the window rows only; otherwise every row (modes outside the window then see c = 0)
+    Geom gw = g;
+    if (!a.skip_outside) { gw.kcut = g.N; gw.pl_lo = gw.pl_hi = 0; }
+    const long long nrc = nsb_window_rows(gw);
+    for (long long rc0 = (long long)blockIdx.x * NSB_ROWS_PER_CTA; rc0 < nrc; rc0 += (long long)gridDim.x * NSB_ROWS_PER_CTA)
+    for (long long rc = rc0; rc < rc0 + NSB_ROWS_PER_CTA && rc < nrc; ++rc) {
+        int i, j;
+        nsb_window_row(gw, rc, i, j);
+        const long long row = (long long)i * g.N + j;
         const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         const long long base = row * g.nzp, cbase = row * a.c_rs;
         const bool row_in = nsb_in_window(kx, ky, g.kcut);
-        if (!row_in && a.skip_outside) continue;
         const int nk = a.skip_outside ? nsb_kz_count(g) : g.nzf;
         for (int k = threadIdx.x; k < nk; k += blockDim.x) {
             const long long e = base + k;
