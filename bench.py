@@ -333,7 +333,7 @@ def ours(args):
         if world == 1 and not args.no_cpu:
             try:
                 p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                                    "--budget", "25", "--n", str(n)], capture_output=True, text=True, timeout=600)
+                                    "--budget", "25", "--grid", str(n)], capture_output=True, text=True, timeout=600)
                 line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
                 out["cpu_baseline"] = json.loads(line).get("cpu_baseline", {"unavailable": json.loads(line).get("unavailable")})
             except Exception as ex:   # the bench line must still be printed
@@ -349,7 +349,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="grid size (default: the BASELINE workload, 512)")
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=512,
+                    help="grid size (default: the BASELINE workload, 512); use --grid under torchrun, which claims --n")
     ap.add_argument("--budget", type=float, default=150.0, help="reference arm: seconds of CPU work for all steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
