@@ -149,6 +149,9 @@ struct nsb200_ctx {
     bool use_pipe = false;         // persistent double-buffered strided pass where built (NSB200_PIPE=1 enables; measured equal)
     int pipe_ctas = 0;
     bool u_in_window = false;      // resident state known to vanish outside the cube |k|_inf <= kmax
+    // the RK kernel leaves w = i k x (next input) in the curl buffer: valid for this input / row stride / window mode
+    const cplx* curl_of = nullptr; int curl_rs = 0; bool curl_win = false;
+    bool fuse_curl = true;         // NSB200_NO_FUSE_CURL=1 keeps the separate curl sweep
     int* flag_dev = nullptr;
     size_t field_elems = 0;        // complex elements per planar local field
     cplx* slab = nullptr;          // one allocation for all fields
@@ -449,7 +452,9 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx***
     for (int d = 0; d < 3; ++d) { ca.u[d] = in[d]; ca.w[d] = h->p2p ? h->W[d] : h->R[3 + d]; }
     ca.g = h->geom(in_w);
     ca.w_rs = rs;
-    {
+    const bool have_curl = h->fuse_curl && h->curl_of == in[0] && h->curl_rs == rs && h->curl_win == in_w && !(h->p2p && h->overlap);
+    h->curl_of = nullptr;   // consumed (the buffer is overwritten further down the pipeline)
+    if (!have_curl) {
         // with the overlapped multi-GPU schedule the curl runs on the second stream, beside the y pass of u
         cudaStream_t cs = (h->p2p && h->overlap) ? h->comm_stream : h->stream;
         if (cs != h->stream) {
@@ -460,9 +465,9 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx***
         ProfScope ps(h, NSB200_PC_CURL, 16.0 * 6.0 * (kw * kw / h->nranks) * nz_in, cs);
         k_curl<<<rg, nsb200_ctx::row_block(nz_in), 0, cs>>>(ca);
         if (cs != h->stream) CK(cudaEventRecord(h->ev_fork, cs));
+        CK(cudaGetLastError());
+        h->launches++;
     }
-    CK(cudaGetLastError());
-    h->launches++;
     cplx* src[6] = {in[0], in[1], in[2], h->R[3], h->R[4], h->R[5]};
     const bool multi = h->nranks > 1;
     //                axis dir  exch            in_rs    out_rs nzv     in_w   out_w  outer_w
@@ -489,7 +494,7 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx***
         xfwd.p2p_out = true;
         if (h->overlap) {
             // Two streams: while one field group drains over NVLink (store phase of the y / forward-x pass), the
-            // other group's HBM-bound local pass runs.  S1 did the curl (launched above on S0? no: see below).
+            // other group's HBM-bound local pass runs.  The curl was launched on S1 above (ev_fork).
             cudaStream_t S0 = h->stream, S1 = h->comm_stream;
             CKR(run_pass(h, yinv_u, srcp, h->R, 0, 3, S0));            // u: needs no curl
             CK(cudaEventRecord(h->ev_a, S0));
@@ -565,6 +570,18 @@ static int rk_stage(nsb200_ctx* h, int stage, double dt, int c_rs, bool in_w, cp
     a.g = h->geom(out_w);
     a.c_rs = c_rs;
     a.skip_outside = (out_w && in_w && h->prune && stage != 4) ? 1 : 0;
+    if (h->fuse_curl && stage != 4) {
+        // the next evaluation's input (TMP, or U after the final update) gets its curl written here; same
+        // buffer, row stride and window mode that rhs_raw would use for it
+        const bool next_w = in_w && h->prune;
+        const int next_rs = (next_w && out_w) ? h->nzc : h->nzp;
+        if (next_rs == c_rs && (a.skip_outside || !next_w)) {
+            for (int d = 0; d < 3; ++d) a.w[d] = h->p2p ? h->W[d] : h->R[3 + d];
+            a.w_rs = next_rs;
+            h->curl_of = (stage == 3) ? h->U[0] : h->TMP[0];
+            h->curl_rs = next_rs; h->curl_win = next_w;
+        }
+    }
     a.stage = stage;
     a.dealias = h->dealias;
     a.kmax2 = h->kmax2;
@@ -577,7 +594,7 @@ static int rk_stage(nsb200_ctx* h, int stage, double dt, int c_rs, bool in_w, cp
         const double kw = a.skip_outside ? 2.0 * h->kmax + 1 : h->N;
         const double nk = a.skip_outside ? h->kmax + 1 : h->nzf;
         const double nc = out_w ? (2.0 * h->kmax + 1) * (2.0 * h->kmax + 1) * (h->kmax + 1) / h->nranks : (double)h->nrows() * h->nzf;
-        const double arrays = stage == 0 ? 9.0 : stage == 3 ? 9.0 : stage == 4 ? 3.0 : 12.0;   // besides c: u, acc, tmp reads/writes
+        const double arrays = (stage == 0 ? 9.0 : stage == 3 ? 9.0 : stage == 4 ? 3.0 : 12.0) + (a.w[0] ? 3.0 : 0.0);   // besides c: u, acc, tmp (, w)
         ProfScope ps(h, NSB200_PC_RK, 16.0 * (3.0 * nc + arrays * (kw * kw / h->nranks) * nk));
         k_rk_stage<<<h->row_grid(), nsb200_ctx::row_block(a.skip_outside ? h->kmax + 1 : h->nzf), 0, h->stream>>>(a);
     }
@@ -621,12 +638,14 @@ static int check_state_support(nsb200_ctx* h) {
 
 // forward / inverse 3-D transforms of 3 planar fields held in W (single rank), real <-> half complex in place
 static int fft3_r2c_inplace(nsb200_ctx* h) {
+    h->curl_of = nullptr;
     CKR(run_z(h, NSB_Z_R2C, 3, h->W, h->nzp, h->nzf, h->nzf));
     CKR(run_pass_full(h, 'x', FWD, 3, h->W, h->W));
     CKR(run_pass_full(h, 'y', FWD, 3, h->W, h->W));
     return 0;
 }
 static int fft3_c2r_inplace(nsb200_ctx* h) {
+    h->curl_of = nullptr;
     CKR(run_pass_full(h, 'y', INV, 3, h->W, h->W));
     CKR(run_pass_full(h, 'x', INV, 3, h->W, h->W));
     CKR(run_z(h, NSB_Z_C2R, 3, h->W, h->nzp, h->nzf, h->nzf));
@@ -713,6 +732,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     h->nzc = (kmax + 1 + 7) / 8 * 8;
     { const char* e = getenv("NSB200_NO_PRUNE"); h->prune = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_NO_TMA"); h->use_tma = !(e && e[0] == '1'); }
+    { const char* e = getenv("NSB200_NO_FUSE_CURL"); h->fuse_curl = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_PIPE"); h->use_pipe = (e && e[0] == '1'); }
     h->ops = ops;
     h->field_elems = (size_t)h->nx_loc * h->N * h->nzp;
@@ -849,6 +869,7 @@ long nsb200_launch_count(nsb200_ctx* h) { return h ? h->launches : 0; }
 long nsb200_device_bytes(nsb200_ctx* h) { return h ? (long)h->bytes : 0; }
 
 static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
+    h->curl_of = nullptr;   // the staging area overlaps the workspace
     const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
     cplx* stage = h->W[0];   // W is one contiguous 6-field buffer >= the 3-field host layout
     CK(cudaMemcpyAsync(stage, host, n * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
@@ -866,6 +887,7 @@ static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
     return 0;
 }
 static int download_from(nsb200_ctx* h, double* host, cplx* const* src) {
+    h->curl_of = nullptr;
     const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
     cplx* stage = h->W[0];
     if (h->cyclic) {
@@ -927,6 +949,7 @@ int nsb200_apply_dealiasing(nsb200_ctx* h, double* array_host, int array_dim) {
     CKR(set_device(h));
     const size_t n = (size_t)array_dim * h->nx_loc * h->N * h->nzf;
     cplx* stage = h->W[0];
+    h->curl_of = nullptr;
     CK(cudaMemcpyAsync(stage, array_host, n * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
     if (h->dealias == NSB200_DEALIAS_23) {
         k_dealias_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, array_dim, h->geom_api(), h->kmax2, h->nrows());
@@ -1062,6 +1085,7 @@ int nsb200_download_real(nsb200_ctx* h, int which, double* real_host) {
 
 int nsb200_initial_condition(nsb200_ctx* h, const char* name, unsigned long long seed, double kp, double energy) {
     if (!h || !name) return fail("nsb200_initial_condition: null argument");
+    h->curl_of = nullptr;
     CKR(set_device(h));
     const int rg = h->row_grid();
     if (!strcmp(name, "TAYLOR_GREEN") || !strcmp(name, "SHAPIRO")) {
@@ -1168,6 +1192,7 @@ int nsb200_profile_read(nsb200_ctx* h, double ms[NSB200_PC_COUNT], long counts[N
 
 int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_ms) {
     if (!h || !elapsed_ms) return fail("nsb200_time_op: null argument");
+    if (op != NSB200_OP_RK4_STEP) h->curl_of = nullptr;   // the single-kernel ops run on the workspace
     if (iters < 1) return fail("nsb200_time_op: iters must be >= 1");
     CKR(set_device(h));
     if (op == NSB200_OP_L2_FLUSH && !h->flush_buf) {

@@ -211,6 +211,8 @@ struct RkArgs {
     int hyper2;          // visc_pow == 2 (pow(k_sqr, 2.0), solver.c:594)
     int c_rs;            // row stride of c (complex elements)
     int skip_outside;    // modes outside the support window are exact zeros in u/tmp/acc: leave them alone
+    cplx* w[3];          // when non-null: also emit w = i k x (next stage input), saving the separate curl sweep
+    int w_rs;            // (may alias c element for element: each thread reads c[e] before it writes w[e])
     double dt, nu, visc_pow, norm;
 };
 
@@ -274,7 +276,8 @@ __global__ void k_rk_stage(const RkArgs a) {
                     cplx bk = rmul(bcoef, c[d]);
                     if (a.euler) bk = rmul(a.dt, bk);
                     a.acc[d][e] = (a.stage == 0) ? bk : caddr(a.acc[d][e], bk);
-                    a.tmp[d][e] = caddr(a.u[d][e], rmul(acoef, c[d]));
+                    c[d] = caddr(a.u[d][e], rmul(acoef, c[d]));   // next stage input
+                    a.tmp[d][e] = c[d];
                 }
             } else {
                 double f1 = 1.0, f2 = 1.0;
@@ -294,8 +297,15 @@ __global__ void k_rk_stage(const RkArgs a) {
                     if (a.euler) bk = rmul(a.dt, bk);
                     const cplx comb = caddr(a.acc[d][e], bk);
                     const cplx u = a.u[d][e];
-                    a.uout[d][e] = a.euler ? caddr(u, comb) : caddr(rmul(f1, u), rmul(f2, comb));
+                    c[d] = a.euler ? caddr(u, comb) : caddr(rmul(f1, u), rmul(f2, comb));   // new state = next step's input
+                    a.uout[d][e] = c[d];
                 }
+            }
+            if (a.w[0]) {
+                cplx wx, wy, wz;
+                curl_mode(kx, ky, k, c[0], c[1], c[2], wx, wy, wz);                  // solver.c:645-647 for the next evaluation
+                const long long we = row * a.w_rs + k;
+                a.w[0][we] = wx; a.w[1][we] = wy; a.w[2][we] = wz;
             }
         }
     }
