@@ -87,6 +87,12 @@ class RefSolver:
     def nonlinear_timing(self):
         self.lib.ref_nonlinear_inplace_timing()
 
+    def fft_seconds(self, reset=True):
+        """Seconds spent inside the (threaded) shim transforms since the last reset."""
+        self.lib.nsb_shim_fft_seconds.restype = ctypes.c_double
+        self.lib.nsb_shim_fft_seconds.argtypes = [ctypes.c_int]
+        return float(self.lib.nsb_shim_fft_seconds(1 if reset else 0))
+
     def measure(self):
         """(E, Omega, P, H, eps) exactly as ComputeSystemMeasurables stores them (literal F4)."""
         out = np.empty(5)

@@ -266,6 +266,11 @@ static void swap01(const fftw_complex* in, fftw_complex* out, ptrdiff_t n0, ptrd
 			memcpy(out + ((size_t)b * n0 + a) * inner, in + ((size_t)a * n1 + b) * inner, sizeof(fftw_complex) * inner);
 }
 
+/* seconds spent inside fftw_mpi_execute_* (threaded) since the last reset: lets the CPU baseline separate the
+ * transforms from the reference's own (serial per rank) loops */
+static double g_fft_seconds = 0.0;
+double nsb_shim_fft_seconds(int reset) { double t = g_fft_seconds; if (reset) g_fft_seconds = 0.0; return t; }
+
 /* ------------------------------------------------------------------ public FFTW symbols */
 void fftw_mpi_init(void) {}
 void fftw_mpi_cleanup(void) {}
@@ -318,6 +323,7 @@ fftw_plan fftw_mpi_plan_many_dft_c2r(int rnk, const ptrdiff_t* n, ptrdiff_t howm
 }
 
 void fftw_mpi_execute_dft_r2c(const fftw_plan p, double* in, fftw_complex* out) {
+	const double t_begin = omp_get_wtime();
 	const ptrdiff_t n0 = p->n[0], n1 = p->n[1], n2 = p->n[2], hm = p->howmany;
 	const ptrdiff_t nzf = n2 / 2 + 1, inner = nzf * hm;
 	const int transposed = (p->flags & FFTW_MPI_TRANSPOSED_OUT) != 0;
@@ -327,9 +333,11 @@ void fftw_mpi_execute_dft_r2c(const fftw_plan p, double* in, fftw_complex* out) 
 	fft_axis(work, n0, (int)n1, inner, -1);                /* axis 1 */
 	fft_axis(work, 1, (int)n0, n1 * inner, -1);            /* axis 0 */
 	if (transposed) { swap01(work, out, n0, n1, inner); fftw_free(work); }  /* out[n1][n0][..] */
+	g_fft_seconds += omp_get_wtime() - t_begin;
 }
 
 void fftw_mpi_execute_dft_c2r(const fftw_plan p, fftw_complex* in, double* out) {
+	const double t_begin = omp_get_wtime();
 	const ptrdiff_t n0 = p->n[0], n1 = p->n[1], n2 = p->n[2], hm = p->howmany;
 	const ptrdiff_t nzf = n2 / 2 + 1, inner = nzf * hm;
 	const int transposed = (p->flags & FFTW_MPI_TRANSPOSED_IN) != 0;
@@ -340,4 +348,5 @@ void fftw_mpi_execute_dft_c2r(const fftw_plan p, fftw_complex* in, double* out) 
 	fft_axis(work, n0, (int)n1, inner, +1);
 	z_c2r(work, out, n0 * n1, (int)n2, (int)hm);
 	fftw_free(work);
+	g_fft_seconds += omp_get_wtime() - t_begin;
 }
