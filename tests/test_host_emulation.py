@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_fft_passes_emulated_on_cpu():
     with tempfile.TemporaryDirectory() as d:
         exe = os.path.join(d, "fft_emul")
-        subprocess.run(["nvcc", "-std=c++17", "-O1", "--extended-lambda", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
+        subprocess.run(["nvcc", "-std=c++17", "-O1", "--extended-lambda", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
                         "-diag-suppress", "20013,20015", "-o", exe, os.path.join(ROOT, "tests", "host_emul", "fft_emul.cu")], check=True)
         p = subprocess.run([exe], capture_output=True, text=True)
         assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout
