@@ -33,6 +33,9 @@ template <int DIR> NSB_HD cplx rot(cplx a) { return DIR == FWD ? mk(a.y, -a.x) :
 template <int DIR> NSB_HD cplx cmul_cs(cplx a, double c, double s) {
     return DIR == FWD ? mk(a.x * c + a.y * s, a.y * c - a.x * s) : mk(a.x * c - a.y * s, a.y * c + a.x * s);
 }
+template <int DIR> NSB_HD cplx cmul_dir(cplx a, cplx w) {   // a * w (FWD) or a * conj(w) (INV)
+    return DIR == FWD ? mk(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x) : mk(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+}
 // table holds exp(-2 pi i m / N); conjugate for the inverse direction
 template <int DIR> NSB_HD cplx twid(const cplx* __restrict__ tw, int idx) {
     cplx w = tw[idx];
@@ -121,18 +124,20 @@ template <int DIR> struct Dft<16, DIR> {
 // ---------------------------------------------------------------------------------------------
 // Plans: N = R1 * R2 * R3 (R3 == 1 for two-pass plans)
 // ---------------------------------------------------------------------------------------------
-template <int N_, int R1_, int R2_, int R3_, int PAD_ = 1> struct FftPlan {
-    static constexpr int N = N_, R1 = R1_, R2 = R2_, R3 = R3_;
-    static constexpr int PASSES = (R3_ > 1) ? 3 : 2;
+template <int N_, int R1_, int R2_, int R3_, int PAD_ = 1, int R4_ = 1> struct FftPlan {
+    static constexpr int N = N_, R1 = R1_, R2 = R2_, R3 = R3_, R4 = R4_;
+    static constexpr int PASSES = (R4_ > 1) ? 4 : ((R3_ > 1) ? 3 : 2);
     static constexpr int M1 = N_ / R1_;                  // row length after pass 1
-    static constexpr int RL = (R3_ > 1) ? R3_ : R2_;     // radix of the last pass
+    static constexpr int RL = (R4_ > 1) ? R4_ : ((R3_ > 1) ? R3_ : R2_);   // radix of the last pass
+    static constexpr int M2 = N_ / (R1_ * R2_);          // sub-row length after pass 2
+    static constexpr int NB3 = N_ / R3_;                 // butterflies of pass 3 (4-pass plans)
     static constexpr int NB1 = N_ / R1_;                 // butterflies per pass
     static constexpr int NB2 = N_ / R2_;
     static constexpr int NBL = N_ / RL;
     static constexpr int ROW = N_ / R1_ + PAD_;          // shared-memory row pitch (PAD_ = 0 for tile-interleaved buffers,
                                                          // which are conflict free without padding and can be filled in place)
     static constexpr int NPAD = R1_ * ROW;               // shared-memory elements per transform
-    static_assert(R1_ * R2_ * R3_ == N_, "bad plan");
+    static_assert(R1_ * R2_ * R3_ * R4_ == N_, "bad plan");
 };
 
 // throughput plans (strided x / y passes): large radices, few passes
@@ -143,7 +148,11 @@ template <> struct BigPlan<64> { typedef FftPlan<64, 8, 8, 1, 0> type; };
 template <> struct BigPlan<128> { typedef FftPlan<128, 8, 16, 1, 0> type; };
 template <> struct BigPlan<256> { typedef FftPlan<256, 16, 16, 1, 0> type; };
 template <> struct BigPlan<512> { typedef FftPlan<512, 8, 8, 8, 0> type; };
+#ifndef NSB_BIG1024_4PASS
 template <> struct BigPlan<1024> { typedef FftPlan<1024, 8, 8, 16, 0> type; };
+#else   // measured slower (1024 threads per tile at 64 registers): y pass 48.6 vs 45.4 ms per step at 1024^3
+template <> struct BigPlan<1024> { typedef FftPlan<1024, 8, 4, 4, 0, 8> type; };
+#endif
 
 // z-pencil plans: R1 is the smallest radix so pass 1 has exactly one butterfly per thread with
 // TP = N/R1 threads per transform (later passes use a subset of the threads)
@@ -164,7 +173,7 @@ template <> struct ZFPlan<64> { typedef FftPlan<64, 8, 8, 1> type; };
 template <> struct ZFPlan<128> { typedef FftPlan<128, 4, 8, 4> type; };
 template <> struct ZFPlan<256> { typedef FftPlan<256, 8, 4, 8> type; };
 template <> struct ZFPlan<512> { typedef FftPlan<512, 8, 8, 8> type; };
-template <> struct ZFPlan<1024> { typedef FftPlan<1024, 16, 4, 16> type; };
+template <> struct ZFPlan<1024> { typedef FftPlan<1024, 8, 4, 4, 1, 8> type; };   // 4 passes, radix <= 8 (the radix-16 plan needed 168 registers)
 
 template <class P> NSB_HD int padi(int i) { return (i / P::M1) * P::ROW + i % P::M1; }
 
@@ -211,17 +220,71 @@ template <class P, int STRIDE> NSB_HD void fft_pass1_scatter(int b, cplx* sm, co
 
 template <class P, int DIR, int STRIDE>
 NSB_HD void fft_pass2(int b, cplx* sm, const cplx* __restrict__ tw) {
-    static_assert(P::PASSES == 3, "pass2 only exists in 3-pass plans");
-    const int k1 = b / P::R3, m2 = b % P::R3;
+    static_assert(P::PASSES >= 3, "pass2 only exists in 3- and 4-pass plans");
+    const int k1 = b / P::M2, m2 = b % P::M2;
     const int base = k1 * P::ROW + m2;
     cplx v[P::R2];
 #pragma unroll
-    for (int j = 0; j < P::R2; ++j) v[j] = sm[(base + j * P::R3) * STRIDE];
+    for (int j = 0; j < P::R2; ++j) v[j] = sm[(base + j * P::M2) * STRIDE];
     Dft<P::R2, DIR>::run(v);
 #pragma unroll
     for (int kp = 1; kp < P::R2; ++kp) v[kp] = cmul(v[kp], twid<DIR>(tw, P::R1 * m2 * kp));
 #pragma unroll
-    for (int kp = 0; kp < P::R2; ++kp) sm[(base + kp * P::R3) * STRIDE] = v[kp];
+    for (int kp = 0; kp < P::R2; ++kp) sm[(base + kp * P::M2) * STRIDE] = v[kp];
+}
+
+// pass 3 of 4-pass plans: in-place R3-point DFTs inside each sub-row (k1, k1') of length M2 = R3*R4, twiddle
+// W_{M2}^{m3 k''} = W_N^{R1 R2 m3 k''}
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass3(int b, cplx* sm, const cplx* __restrict__ tw) {
+    static_assert(P::PASSES == 4, "pass3 only exists in 4-pass plans");
+    const int m3 = b % P::R4, sub = b / P::R4;          // sub = k1 * R2 + k1'
+    const int k1 = sub / P::R2, k1p = sub % P::R2;
+    const int base = k1 * P::ROW + k1p * P::M2 + m3;
+    cplx v[P::R3];
+#pragma unroll
+    for (int j = 0; j < P::R3; ++j) v[j] = sm[(base + j * P::R4) * STRIDE];
+    Dft<P::R3, DIR>::run(v);
+#pragma unroll
+    for (int kq = 1; kq < P::R3; ++kq) v[kq] = cmul(v[kq], twid<DIR>(tw, P::R1 * P::R2 * m3 * kq));
+#pragma unroll
+    for (int kq = 0; kq < P::R3; ++kq) sm[(base + kq * P::R4) * STRIDE] = v[kq];
+}
+
+// ---- mid passes with ONE base twiddle per butterfly in registers; the higher powers are formed by multiplication
+// (radix <= 4 mid passes of the 4-pass plans: two extra complex multiplies instead of per-lane table fetches)
+template <int R, int DIR> NSB_HD void twiddle_powers(cplx* v, cplx w1) {
+    cplx w = w1;
+#pragma unroll
+    for (int k = 1; k < R; ++k) {
+        v[k] = cmul_dir<DIR>(v[k], w);
+        if (k + 1 < R) w = cmul(w, w1);
+    }
+}
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass2_w1(int b, cplx* sm, cplx w1) {      // w1 = tw[R1 * (b % M2)]
+    const int k1 = b / P::M2, m2 = b % P::M2;
+    const int base = k1 * P::ROW + m2;
+    cplx v[P::R2];
+#pragma unroll
+    for (int j = 0; j < P::R2; ++j) v[j] = sm[(base + j * P::M2) * STRIDE];
+    Dft<P::R2, DIR>::run(v);
+    twiddle_powers<P::R2, DIR>(v, w1);
+#pragma unroll
+    for (int kp = 0; kp < P::R2; ++kp) sm[(base + kp * P::M2) * STRIDE] = v[kp];
+}
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass3_w1(int b, cplx* sm, cplx w1) {      // w1 = tw[R1 * R2 * (b % R4)]
+    const int m3 = b % P::R4, sub = b / P::R4;
+    const int k1 = sub / P::R2, k1p = sub % P::R2;
+    const int base = k1 * P::ROW + k1p * P::M2 + m3;
+    cplx v[P::R3];
+#pragma unroll
+    for (int j = 0; j < P::R3; ++j) v[j] = sm[(base + j * P::R4) * STRIDE];
+    Dft<P::R3, DIR>::run(v);
+    twiddle_powers<P::R3, DIR>(v, w1);
+#pragma unroll
+    for (int kq = 0; kq < P::R3; ++kq) sm[(base + kq * P::R4) * STRIDE] = v[kq];
 }
 
 // ---- passes with the (loop invariant) twiddles of this thread held in registers
@@ -233,10 +296,7 @@ template <class P> NSB_HD void load_tw_pass1(int b, const cplx* __restrict__ tw,
 // pass 2 twiddles of butterfly b: W_N^{R1 (b % R3) kp}, kp = 1..R2-1
 template <class P> NSB_HD void load_tw_pass2(int b, const cplx* __restrict__ tw, cplx* w) {
 #pragma unroll
-    for (int kp = 1; kp < P::R2; ++kp) w[kp - 1] = tw[P::R1 * (b % P::R3) * kp];
-}
-template <int DIR> NSB_HD cplx cmul_dir(cplx a, cplx w) {   // a * w (FWD) or a * conj(w) (INV)
-    return DIR == FWD ? mk(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x) : mk(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+    for (int kp = 1; kp < P::R2; ++kp) w[kp - 1] = tw[P::R1 * (b % P::M2) * kp];
 }
 template <class P, int DIR, int STRIDE, class Ld>
 NSB_HD void fft_pass1_rw(int b, cplx* sm, const cplx* w, Ld ld) {
@@ -256,24 +316,33 @@ template <class P, int DIR> NSB_HD void fft_pass1_regs_rw(cplx* v, const cplx* w
 }
 template <class P, int DIR, int STRIDE>
 NSB_HD void fft_pass2_rw(int b, cplx* sm, const cplx* w) {
-    static_assert(P::PASSES == 3, "pass2 only exists in 3-pass plans");
-    const int k1 = b / P::R3, m2 = b % P::R3;
+    static_assert(P::PASSES >= 3, "pass2 only exists in 3- and 4-pass plans");
+    const int k1 = b / P::M2, m2 = b % P::M2;
     const int base = k1 * P::ROW + m2;
     cplx v[P::R2];
 #pragma unroll
-    for (int j = 0; j < P::R2; ++j) v[j] = sm[(base + j * P::R3) * STRIDE];
+    for (int j = 0; j < P::R2; ++j) v[j] = sm[(base + j * P::M2) * STRIDE];
     Dft<P::R2, DIR>::run(v);
 #pragma unroll
     for (int kp = 1; kp < P::R2; ++kp) v[kp] = cmul_dir<DIR>(v[kp], w[kp - 1]);
 #pragma unroll
-    for (int kp = 0; kp < P::R2; ++kp) sm[(base + kp * P::R3) * STRIDE] = v[kp];
+    for (int kp = 0; kp < P::R2; ++kp) sm[(base + kp * P::M2) * STRIDE] = v[kp];
+}
+
+// start of the RL contiguous elements the last pass of butterfly b works on (b = k1 + R1*k1' [+ R1*R2*k1''])
+template <class P> NSB_HD int fft_row_base(int b) {
+    if constexpr (P::PASSES == 4) {
+        const int k1 = b % P::R1, r = b / P::R1;
+        return k1 * P::ROW + (r % P::R2) * P::M2 + (r / P::R2) * P::RL;
+    } else {
+        return (b % P::R1) * P::ROW + (b / P::R1) * P::RL;
+    }
 }
 
 // last pass: v[k2] is output element  b + k2 * P::NBL
 template <class P, int DIR, int STRIDE>
 NSB_HD void fft_pass_last(int b, const cplx* sm, cplx* v) {
-    const int k1 = b % P::R1, kp = b / P::R1;
-    const int base = k1 * P::ROW + kp * P::RL;
+    const int base = fft_row_base<P>(b);
 #pragma unroll
     for (int m = 0; m < P::RL; ++m) v[m] = sm[(base + m) * STRIDE];
     Dft<P::RL, DIR>::run(v);

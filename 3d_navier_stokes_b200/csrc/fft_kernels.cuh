@@ -173,8 +173,12 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a, con
     }
     __syncthreads();
 #endif
-    if constexpr (P::PASSES == 3) {
+    if constexpr (P::PASSES >= 3) {
         for (int b = q; b < P::NB2; b += TP) fft_pass2<P, DIR, T>(b, sm, tw);
+        __syncthreads();
+    }
+    if constexpr (P::PASSES == 4) {
+        for (int b = q; b < P::NB3; b += TP) fft_pass3<P, DIR, T>(b, sm, tw);
         __syncthreads();
     }
     const int slo = a.out_skip_lo, shi = a.out_skip_hi;
@@ -418,8 +422,14 @@ NSB_HD cplx cross_comp(cplx a1, cplx b2, cplx a2, cplx b1) {
 // last inverse pass is the one that consumes them in the first forward pass: the last inverse pass
 // writes its outputs back IN PLACE (its own shared-memory row), no natural-order shuffle is needed and
 // the six real-space fields of the pair never leave the SM.
+// registers a thread must be allowed to keep (decides how many CTAs the register allocation admits per SM);
+// measured: 512 -> 3 CTAs x 192 threads at 96 registers, 1024 -> 2 CTAs x 384 threads at 80 registers
 #ifndef NSB_ZF_MIN_REGS
-#define NSB_ZF_MIN_REGS 104
+#define NSB_ZF_MIN_REGS(N) ((N) >= 1024 ? 80 : 104)
+#else
+#define NSB_ZF_MIN_REGS_FIXED NSB_ZF_MIN_REGS
+#undef NSB_ZF_MIN_REGS
+#define NSB_ZF_MIN_REGS(N) NSB_ZF_MIN_REGS_FIXED
 #endif
 template <class P> struct ZFusedCfg {
     static_assert(P::R1 == P::RL, "fused z kernel needs a balanced plan (first radix == last radix)");
@@ -431,7 +441,7 @@ template <class P> struct ZFusedCfg {
     // that a thread keeps >= NSB_ZF_MIN_REGS registers (80 spilled 260 B/thread to L2: see profiles/)
     static constexpr int SMEM = 6 * P::NPAD * G * 16;
     static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
-    static constexpr int BY_REGS = 65536 / (THREADS * NSB_ZF_MIN_REGS);
+    static constexpr int BY_REGS = 65536 / (THREADS * NSB_ZF_MIN_REGS(P::N));
     static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
 };
 
@@ -447,14 +457,24 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
     const cplx* __restrict__ tw = a.tw;
     const int kzin = a.kz_in, kzout = a.kz_out;
     // this thread's row in the in-place layout (same indexing as fft_pass_last with b = q)
-    const int rowbase = (q % P::R1) * P::ROW + (q / P::R1) * P::RL;
+    const int rowbase = fft_row_base<P>(q);
     // Loop-invariant twiddles of this thread live in registers: in this kernel every lane needs different
     // table entries, so fetching them per pass cost more L1 cycles than the data exchange (profiles/).
-    constexpr bool RW2 = (P::PASSES == 3) && (P::NB2 == TP);   // one pass-2 butterfly per thread
+    constexpr bool RW2 = (P::PASSES == 3) && (P::NB2 == TP);   // one pass-2 butterfly per thread: all its twiddles
+    constexpr bool W1 = (P::PASSES == 4);                      // 4-pass plans: one base twiddle per mid-pass butterfly
+    constexpr int MID2 = W1 ? P::NB2 / TP : 1, MID3 = W1 ? P::NB3 / TP : 1;
+    static_assert(!W1 || (P::NB2 % TP == 0 && P::NB3 % TP == 0), "mid passes must split evenly over the team");
     cplx tw1[P::R1 - 1];
     cplx tw2[RW2 ? P::R2 - 1 : 1];
+    cplx b2[MID2], b3[MID3];
     load_tw_pass1<P>(q, tw, tw1);
     if constexpr (RW2) load_tw_pass2<P>(q, tw, tw2);
+    if constexpr (W1) {
+#pragma unroll
+        for (int i = 0; i < MID2; ++i) b2[i] = tw[P::R1 * ((q + i * TP) % P::M2)];
+#pragma unroll
+        for (int i = 0; i < MID3; ++i) b3[i] = tw[P::R1 * P::R2 * ((q + i * TP) % P::R4)];
+    }
     for (long long pr0 = (long long)blockIdx.x * G; pr0 < a.npairs; pr0 += (long long)gridDim.x * G) {
         const long long pr = pr0 + s;
         const bool ok = pr < a.npairs;
@@ -474,12 +494,25 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
             }
         }
         __syncthreads();
-        if constexpr (P::PASSES == 3) {
+        if constexpr (P::PASSES >= 3) {
             if (ok) {
 #pragma unroll 1
                 for (int ff = 0; ff < 2; ++ff) {
                     if constexpr (RW2) fft_pass2_rw<P, INV, 1>(q, sm + (2 * t + ff) * NP, tw2);
-                    else for (int b = q; b < P::NB2; b += TP) fft_pass2<P, INV, 1>(b, sm + (2 * t + ff) * NP, tw);
+                    else if constexpr (W1) {
+#pragma unroll
+                        for (int i = 0; i < MID2; ++i) fft_pass2_w1<P, INV, 1>(q + i * TP, sm + (2 * t + ff) * NP, b2[i]);
+                    } else for (int b = q; b < P::NB2; b += TP) fft_pass2<P, INV, 1>(b, sm + (2 * t + ff) * NP, tw);
+                }
+            }
+            __syncthreads();
+        }
+        if constexpr (P::PASSES == 4) {
+            if (ok) {
+#pragma unroll 1
+                for (int ff = 0; ff < 2; ++ff) {
+#pragma unroll
+                    for (int i = 0; i < MID3; ++i) fft_pass3_w1<P, INV, 1>(q + i * TP, sm + (2 * t + ff) * NP, b3[i]);
                 }
             }
             __syncthreads();
@@ -511,10 +544,20 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
         __syncthreads();
         if (ok) fft_pass1_scatter<P, 1>(q, sm + t * NP, c);
         __syncthreads();
-        if constexpr (P::PASSES == 3) {
+        if constexpr (P::PASSES >= 3) {
             if (ok) {
                 if constexpr (RW2) fft_pass2_rw<P, FWD, 1>(q, sm + t * NP, tw2);
-                else for (int b = q; b < P::NB2; b += TP) fft_pass2<P, FWD, 1>(b, sm + t * NP, tw);
+                else if constexpr (W1) {
+#pragma unroll
+                    for (int i = 0; i < MID2; ++i) fft_pass2_w1<P, FWD, 1>(q + i * TP, sm + t * NP, b2[i]);
+                } else for (int b = q; b < P::NB2; b += TP) fft_pass2<P, FWD, 1>(b, sm + t * NP, tw);
+            }
+            __syncthreads();
+        }
+        if constexpr (P::PASSES == 4) {
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < MID3; ++i) fft_pass3_w1<P, FWD, 1>(q + i * TP, sm + t * NP, b3[i]);
             }
             __syncthreads();
         }
@@ -536,7 +579,7 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
                 if (k <= N / 2 && k < kzout) {
                     const int m = (N - k) & (N - 1);          // partner Z(N - k) sits in the row of thread m % NBL
                     const int qm = m % P::NBL, jm = m / P::NBL;
-                    const cplx Zm = buf[(qm % P::R1) * P::ROW + (qm / P::R1) * P::RL + jm];
+                    const cplx Zm = buf[fft_row_base<P>(qm) + jm];
                     cplx A, B;
                     unpack_pair(v[j], Zm, A, B);
                     ra[k] = A;
@@ -549,6 +592,9 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
 }
 
 // ------------------------------------------------------------------------------ launch helpers
+#ifndef NSB_STRIDED_TP_1024
+#define NSB_STRIDED_TP_1024 64
+#endif
 template <int N> struct StridedCfg;
 template <> struct StridedCfg<16> { static constexpr int T = 8, TP = 4; };
 template <> struct StridedCfg<32> { static constexpr int T = 8, TP = 4; };
@@ -556,4 +602,4 @@ template <> struct StridedCfg<64> { static constexpr int T = 8, TP = 8; };
 template <> struct StridedCfg<128> { static constexpr int T = 8, TP = 8; };
 template <> struct StridedCfg<256> { static constexpr int T = 8, TP = 16; };
 template <> struct StridedCfg<512> { static constexpr int T = 8, TP = 32; };
-template <> struct StridedCfg<1024> { static constexpr int T = 8, TP = 64; };   // 128-byte segments (T = 4 halved the DRAM efficiency)
+template <> struct StridedCfg<1024> { static constexpr int T = 8, TP = NSB_STRIDED_TP_1024; };   // 128-byte segments (T = 4 halved the DRAM efficiency)

@@ -25,8 +25,16 @@ template <class P, int DIR, int STRIDE> double run_plan() {
     } else {
         for (int b = 0; b < P::NB1; ++b) fft_pass1<P, DIR, STRIDE>(b, s, tw.data(), [&](int n) { return x[n]; });
     }
-    if constexpr (P::PASSES == 3)
-        for (int b = 0; b < P::NB2; ++b) fft_pass2<P, DIR, STRIDE>(b, s, tw.data());
+    if constexpr (P::PASSES >= 3)
+        for (int b = 0; b < P::NB2; ++b) {
+            if constexpr (P::PASSES == 4) fft_pass2_w1<P, DIR, STRIDE>(b, s, tw[P::R1 * (b % P::M2)]);
+            else fft_pass2<P, DIR, STRIDE>(b, s, tw.data());
+        }
+    if constexpr (P::PASSES == 4)
+        for (int b = 0; b < P::NB3; ++b) {
+            if (b & 1) fft_pass3_w1<P, DIR, STRIDE>(b, s, tw[P::R1 * P::R2 * (b % P::R4)]);
+            else fft_pass3<P, DIR, STRIDE>(b, s, tw.data());
+        }
     for (int b = 0; b < P::NBL; ++b) {
         cplx v[P::RL];
         fft_pass_last<P, DIR, STRIDE>(b, s, v);
@@ -110,7 +118,7 @@ template <class P> int check_fused() {
     }
     std::vector<cplx> rows[6][2], outA[3], outB[3];
     for (int f = 0; f < 6; ++f) for (int r = 0; r < 2; ++r) { rows[f][r].resize(N / 2 + 1); for (auto& z : rows[f][r]) z = mk(frand(), frand()); }
-    auto rowbase = [](int q) { return (q % P::R1) * (P::M1 + 1) + (q / P::R1) * P::RL; };
+    auto rowbase = [](int q) { return fft_row_base<P>(q); };
     // inverse
     for (int t = 0; t < 3; ++t) for (int ff = 0; ff < 2; ++ff) for (int q = 0; q < TP; ++q) {
         int f = 2 * t + ff;
@@ -118,11 +126,14 @@ template <class P> int check_fused() {
         fft_pass1_rw<P, INV, 1>(q, sm.data() + f * NP, w1, [&](int n) { int k = n <= N / 2 ? n : N - n; return pack_hermitian<N>(n, rows[f][0][k], rows[f][1][k]); });
     }
     constexpr bool RW2 = (P::PASSES == 3) && (P::NB2 == TP);
-    if constexpr (P::PASSES == 3)
+    if constexpr (P::PASSES >= 3)
         for (int f = 0; f < 6; ++f) for (int b = 0; b < P::NB2; ++b) {
             if constexpr (RW2) { cplx w2[P::R2 - 1]; load_tw_pass2<P>(b, tw.data(), w2); fft_pass2_rw<P, INV, 1>(b, sm.data() + f * NP, w2); }
+            else if constexpr (P::PASSES == 4) fft_pass2_w1<P, INV, 1>(b, sm.data() + f * NP, tw[P::R1 * (b % P::M2)]);
             else fft_pass2<P, INV, 1>(b, sm.data() + f * NP, tw.data());
         }
+    if constexpr (P::PASSES == 4)
+        for (int f = 0; f < 6; ++f) for (int b = 0; b < P::NB3; ++b) fft_pass3_w1<P, INV, 1>(b, sm.data() + f * NP, tw[P::R1 * P::R2 * (b % P::R4)]);
     for (int f = 0; f < 6; ++f) for (int q = 0; q < TP; ++q) {
         cplx v[P::RL]; fft_pass_last<P, INV, 1>(q, sm.data() + f * NP, v);
         for (int j = 0; j < P::RL; ++j) sm[f * NP + rowbase(q) + j] = v[j];
@@ -154,11 +165,14 @@ template <class P> int check_fused() {
         for (int j = 0; j < P::R1; ++j) creg[t * TP + q][j] = c[j];
     }
     for (int t = 0; t < 3; ++t) for (int q = 0; q < TP; ++q) fft_pass1_scatter<P, 1>(q, sm.data() + t * NP, creg[t * TP + q].data());
-    if constexpr (P::PASSES == 3)
+    if constexpr (P::PASSES >= 3)
         for (int t = 0; t < 3; ++t) for (int b = 0; b < P::NB2; ++b) {
             if constexpr (RW2) { cplx w2[P::R2 - 1]; load_tw_pass2<P>(b, tw.data(), w2); fft_pass2_rw<P, FWD, 1>(b, sm.data() + t * NP, w2); }
+            else if constexpr (P::PASSES == 4) fft_pass2_w1<P, FWD, 1>(b, sm.data() + t * NP, tw[P::R1 * (b % P::M2)]);
             else fft_pass2<P, FWD, 1>(b, sm.data() + t * NP, tw.data());
         }
+    if constexpr (P::PASSES == 4)
+        for (int t = 0; t < 3; ++t) for (int b = 0; b < P::NB3; ++b) fft_pass3_w1<P, FWD, 1>(b, sm.data() + t * NP, tw[P::R1 * P::R2 * (b % P::R4)]);
     std::vector<std::vector<cplx>> vreg(3 * TP, std::vector<cplx>(P::RL));
     for (int t = 0; t < 3; ++t) for (int q = 0; q < TP; ++q) {
         cplx v[P::RL]; fft_pass_last<P, FWD, 1>(q, sm.data() + t * NP, v);
@@ -204,6 +218,7 @@ int main() {
     bad += check<BigPlan<256>::type>("big");
     bad += check<BigPlan<512>::type>("big");
     bad += check<BigPlan<1024>::type>("big");
+    bad += check<FftPlan<1024, 8, 8, 16, 0>>("big3");
     bad += check<ZPlan<64>::type>("z");
     bad += check<ZPlan<128>::type>("z");
     bad += check<ZPlan<256>::type>("z");
@@ -217,6 +232,10 @@ int main() {
     bad += check_fused<ZFPlan<128>::type>();
     bad += check_fused<ZFPlan<256>::type>();
     bad += check_fused<ZFPlan<512>::type>();
+    bad += check<ZFPlan<1024>::type>("zf4");
+    bad += check<FftPlan<256, 4, 4, 4, 1, 4>>("zf4");
+    bad += check_fused<FftPlan<256, 4, 4, 4, 1, 4>>();
+    bad += check_fused<ZFPlan<1024>::type>();
     bad += check_pack<16>();
     bad += check_pack<64>();
     bad += check_pack<512>();
