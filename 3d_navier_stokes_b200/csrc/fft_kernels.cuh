@@ -424,12 +424,10 @@ NSB_HD cplx cross_comp(cplx a1, cplx b2, cplx a2, cplx b1) {
 // the six real-space fields of the pair never leave the SM.
 // registers a thread must be allowed to keep (decides how many CTAs the register allocation admits per SM);
 // measured: 512 -> 3 CTAs x 192 threads at 96 registers, 1024 -> 2 CTAs x 384 threads at 80 registers
-#ifndef NSB_ZF_MIN_REGS
-#define NSB_ZF_MIN_REGS(N) ((N) >= 1024 ? 80 : 104)
+#ifdef NSB_ZF_MIN_REGS_OVERRIDE   // tuning builds: -DNSB_ZF_MIN_REGS_OVERRIDE=<regs>
+#define NSB_ZF_MIN_REGS(N) NSB_ZF_MIN_REGS_OVERRIDE
 #else
-#define NSB_ZF_MIN_REGS_FIXED NSB_ZF_MIN_REGS
-#undef NSB_ZF_MIN_REGS
-#define NSB_ZF_MIN_REGS(N) NSB_ZF_MIN_REGS_FIXED
+#define NSB_ZF_MIN_REGS(N) ((N) >= 1024 ? 80 : 104)
 #endif
 template <class P> struct ZFusedCfg {
     static_assert(P::R1 == P::RL, "fused z kernel needs a balanced plan (first radix == last radix)");

@@ -218,7 +218,7 @@ def curl_hat(u_hat, N, local_start=0, local_n=None):
     return w
 
 
-def nonlinear_rhs(u_hat, N):
+def nonlinear_rhs(u_hat, N, dealias=True):
     """NonlinearRHSBatch (solver.c:620-731).
 
     The reference's transposed-plan trick (Q8) leaves the real-space scratch x<->y swapped;
@@ -247,7 +247,7 @@ def nonlinear_rhs(u_hat, N):
     out[..., 1] -= KY * k2inv * kdot
     out[..., 2] -= KZ * k2inv * kdot
     out[0, 0, 0, :] = 0.0                             # :713-718
-    return apply_dealiasing(out, N)                   # :727
+    return apply_dealiasing(out, N) if dealias else out   # :727 (dealias=False: the ABI's NSB200_DEALIAS_NONE mode)
 
 
 # --------------------------------------------------------------------------------------
@@ -261,11 +261,11 @@ def viscous_D(N, dt, nu, visc_pow=1.0):
     return dt * (nu * np.power(k2, visc_pow))
 
 
-def rk4_step(u_hat, N, dt, nu, visc_pow=1.0, euler=False):
-    k1 = nonlinear_rhs(u_hat, N)                                 # :522
-    k2 = nonlinear_rhs(u_hat + dt * RK4_A21 * k1, N)             # :531-538
-    k3 = nonlinear_rhs(u_hat + dt * RK4_A32 * k2, N)             # :547-554
-    k4 = nonlinear_rhs(u_hat + dt * RK4_A43 * k3, N)             # :563-570
+def rk4_step(u_hat, N, dt, nu, visc_pow=1.0, euler=False, dealias=True):
+    k1 = nonlinear_rhs(u_hat, N, dealias)                        # :522
+    k2 = nonlinear_rhs(u_hat + dt * RK4_A21 * k1, N, dealias)    # :531-538
+    k3 = nonlinear_rhs(u_hat + dt * RK4_A32 * k2, N, dealias)    # :547-554
+    k4 = nonlinear_rhs(u_hat + dt * RK4_A43 * k3, N, dealias)    # :563-570
     comb = RK4_B1 * k1 + RK4_B2 * k2 + RK4_B3 * k3 + RK4_B4 * k4  # left to right, :601
     if euler:                                                    # :585 (__EULER)
         return u_hat + (dt * (RK4_B1 * k1) + dt * (RK4_B2 * k2) + dt * (RK4_B3 * k3) + dt * (RK4_B4 * k4))

@@ -129,6 +129,24 @@ def test_euler_system_update():
         assert rel(s.get_u_hat(), o.rk4_step(u, N, dt, 0.3, euler=True)) < TOL_FIELD
 
 
+def test_dealias_none_mode_and_undealiased_input():
+    """NSB200_DEALIAS_NONE (not a reference mode: __DEALIAS_23 is forced, data_types.h:63) and a state with energy
+    outside the 2/3 cube: both must take the full, unpruned transforms and still match the restatement."""
+    n = 32; N = (n, n, n); dt = 1e-4
+    rng = np.random.default_rng(3)
+    u = o.c2r(o.random_phase_ic(N, seed=5, kp=6.0), N)                  # real field ...
+    u = o.r2c(u + 1e-3 * rng.standard_normal(u.shape))                   # ... plus broadband noise: energy at every k
+    with nsb.Solver(n, nu=0.02, dealias=False) as s:
+        assert rel(s.nonlinear_rhs_batch(u), o.nonlinear_rhs(u, N, dealias=False)) < TOL_FIELD
+        s.set_u_hat(u)
+        s.rk4_step(dt)
+        assert rel(s.get_u_hat(), o.rk4_step(u, N, dt, 0.02, dealias=False)) < TOL_FIELD
+    with nsb.Solver(n, nu=0.02, dealias=True) as s:                      # dealiasing on, but the INPUT is not dealiased
+        s.set_u_hat(u)
+        s.rk4_step(dt)
+        assert rel(s.get_u_hat(), o.rk4_step(u, N, dt, 0.02)) < TOL_FIELD
+
+
 def test_input_is_preserved_like_fftw_preserve_input():
     n = 32; N = (n, n, n)
     u0 = o.random_phase_ic(N, seed=9, kp=4.0)

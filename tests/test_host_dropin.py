@@ -64,6 +64,33 @@ def test_reference_program_on_gpu_corrected_measures():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(B200), reason="host/_build/solver_b200 not built (make -C host)")
+def test_restart_from_state_file_through_the_z_flag():
+    """`-i TESTING -z <dump>` restarts from a raw u_hat dump.  20 + 20 steps must equal 40 steps."""
+    n = 32
+    common = ["-n", n, "-n", n, "-n", n, "-h", 1e-3, "-v", 0.01, "-p", 5]
+
+    def run(extra, d):
+        env = dict(os.environ, NSB_IO_STUB_DIR=d)
+        p = subprocess.run([B200] + [str(a) for a in common + extra], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        u = np.fromfile(os.path.join(d, "u_hat_final.bin")).view(np.complex128)
+        return u, np.loadtxt(os.path.join(d, "series.txt"))
+
+    with tempfile.TemporaryDirectory() as d1, tempfile.TemporaryDirectory() as d2, tempfile.TemporaryDirectory() as d3:
+        u40, s40 = run(["-s", 0.0, "-e", 0.0405, "-i", "TAYLOR_GREEN"], d1)
+        u20, s20 = run(["-s", 0.0, "-e", 0.0205, "-i", "TAYLOR_GREEN"], d2)
+        ur, sr = run(["-s", 0.0, "-e", 0.0205, "-i", "TESTING", "-z", os.path.join(d2, "u_hat_final.bin")], d3)
+    assert np.abs(u20).max() > 0 and not np.array_equal(u20, u40)
+    assert np.abs(ur - u40).max() <= 1e-13 * np.abs(u40).max()
+    assert sr[0, 1] == pytest.approx(s20[-1, 1], rel=1e-12)        # restart picks up the energy where the first leg ended
+    assert sr[-1, 1] == pytest.approx(s40[-1, 1], rel=1e-12)
+    # a missing file is the reference's own CLI error (utils.c:211-214)
+    p = subprocess.run([B200, "-i", "TESTING", "-z", "/nonexistent/state.bin"], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and "cannot be found" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(B200), reason="host/_build/solver_b200 not built (make -C host)")
 def test_reference_program_error_behaviour_is_kept():
     # utils.c:99-102: odd sizes are rejected by the reference's own CLI check, exit(1)
     p = subprocess.run([B200, "-n", "33"], capture_output=True, text=True, timeout=60)
