@@ -31,6 +31,13 @@ from __future__ import annotations
 
 import numpy as np
 
+try:   # threaded pocketfft when SciPy is there; numpy.fft (also pocketfft) otherwise: same arithmetic
+    import scipy.fft as _fft
+    _KW = {"workers": -1}
+except Exception:   # pragma: no cover
+    _fft = np.fft
+    _KW = {}
+
 # RK4 tableau, solver.c:29-32
 RK4_A21 = 0.5
 RK4_A32 = 0.5
@@ -90,14 +97,14 @@ def apply_dealiasing(arr, N, local_start=0, local_n=None):
 # --------------------------------------------------------------------------------------
 def r2c(u):
     """[Nx][Ny][Nz][3] real -> [Nx][Ny][Nz/2+1][3] complex, unnormalised forward DFT."""
-    return np.fft.rfftn(u, axes=(0, 1, 2))
+    return _fft.rfftn(u, axes=(0, 1, 2), **_KW)
 
 
 def c2r(u_hat, N):
     """Unnormalised inverse (FFTW c2r): result = N^3 * irfftn.  Like FFTW/pocketfft the
     imaginary parts of the kz=0 / kz=Nz/2 elements are ignored on the last axis."""
     Nx, Ny, Nz = N
-    return np.fft.irfftn(u_hat, s=(Nx, Ny, Nz), axes=(0, 1, 2)) * float(Nx * Ny * Nz)
+    return _fft.irfftn(u_hat, s=(Nx, Ny, Nz), axes=(0, 1, 2), **_KW) * float(Nx * Ny * Nz)
 
 
 # --------------------------------------------------------------------------------------

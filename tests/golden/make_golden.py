@@ -36,12 +36,12 @@ np.savez_compressed({os.path.join(HERE, tag + '.npz')!r}, n=n, nu={nu}, dt={dt},
     subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)
 
 
-def series_case(tag, n, nu, dt, T, save_every):
+def series_case(tag, n, nu, dt, T, save_every, keep_state=True):
     code = f"""
 import sys; sys.path.insert(0, {os.path.join(ROOT, 'oracle')!r})
 import numpy as np, ref_lib as R
 series, uh, nw = R.run_main(['-n',{n},'-n',{n},'-n',{n},'-s',0.0,'-e',{T},'-h',{dt},'-v',{nu},'-i','TAYLOR_GREEN','-p',{save_every}])
-np.savez_compressed({os.path.join(HERE, tag + '.npz')!r}, n={n}, nu={nu}, dt={dt}, T={T}, save_every={save_every}, series=series, u_final=uh.reshape({n},{n},{n}//2+1,3), n_writes=nw)
+np.savez_compressed({os.path.join(HERE, tag + '.npz')!r}, n={n}, nu={nu}, dt={dt}, T={T}, save_every={save_every}, series=series, u_final=(uh.reshape({n},{n},{n}//2+1,3) if {keep_state} else np.zeros(0)), n_writes=nw)
 """
     subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)
 
@@ -54,6 +54,8 @@ if __name__ == "__main__":
     one_case("ref_rp16_hyper", 16, 0.001, 1e-3, "RANDOM_PHASE", hyper=True)
     # whole program (main.c -> SpectralSolve), Taylor-Green 32^3, 40 steps, save every 4 (BASELINE config 1 in small)
     series_case("ref_main_tg32", 32, 0.01, 1e-3, 0.0405, 4)
+    # BASELINE configs[1]: Taylor-Green 256^3, nu = 1/1600, dt = 1e-3, 20 steps, series only (the state is 400 MB)
+    series_case("ref_main_tg256_series", 256, 1.0 / 1600.0, 1e-3, 0.0205, 5, keep_state=False)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

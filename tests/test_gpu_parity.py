@@ -284,6 +284,26 @@ def test_golden_whole_program_series():
     assert np.allclose(ser[:, [0, 1, 2, 3, 5]], ref[:, [0, 1, 2, 3, 5]], rtol=TOL_SERIES, atol=0)
 
 
+def test_config2_taylor_green_256_series_vs_reference_build():
+    """BASELINE configs[1]: Taylor-Green 256^3, nu = 1/1600, dt = 1e-3 on one B200; energy / enstrophy / dissipation series
+    against the series the reference's own C produced for the same argv (tests/golden/ref_main_tg256_series.npz)."""
+    g = np.load(os.path.join(G, "ref_main_tg256_series.npz"))
+    n = int(g["n"])
+    with nsb.Solver(n, nu=float(g["nu"])) as s:
+        s.initial_conditions("TAYLOR_GREEN")
+        lit = nsb.spectral_solve(s, 0.0, float(g["T"]), float(g["dt"]), save_every=int(g["save_every"]), literal=True)
+        s.initial_conditions("TAYLOR_GREEN")
+        cor = nsb.spectral_solve(s, 0.0, float(g["T"]), float(g["dt"]), save_every=int(g["save_every"]), literal=False)
+    ref = g["series"]
+    assert lit.shape == ref.shape == (5, 6)
+    assert np.allclose(lit[:, [0, 1, 2, 3, 5]], ref[:, [0, 1, 2, 3, 5]], rtol=TOL_SERIES, atol=0)
+    # corrected sums: E(0) = pi^3, and dE/dt = -eps (trapezoid over the run)
+    assert cor[0, 1] == pytest.approx(PI3, rel=1e-12)
+    de = (cor[0, 1] - cor[-1, 1]) / (cor[-1, 0] - cor[0, 0])
+    trap = float(np.sum(0.5 * (cor[1:, 5] + cor[:-1, 5]) * np.diff(cor[:, 0])))
+    assert de == pytest.approx(trap / (cor[-1, 0] - cor[0, 0]), rel=1e-5)
+
+
 # ----------------------------------------------------------------------------- the reference build itself, when its .so travelled
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref/libns_ref.so not present")
 def test_against_reference_build_64():
