@@ -122,6 +122,9 @@ def mem_available_gb():
 def reference_arm(n, steps, warmup, budget_s, n_gpus):
     """Times the reference's own RK4Step / NonlinearRHSBatch (oracle/_ref) on the host cores."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and may use every core
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncores)
     import ref_lib as R
     base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
