@@ -148,6 +148,7 @@ struct nsb200_ctx {
     bool use_tma = true;           // TMA tile loads in the strided passes (NSB200_NO_TMA=1: cp.async path)
     bool use_pipe = false;         // persistent double-buffered strided pass where built (NSB200_PIPE=1 enables; measured equal)
     int pipe_ctas = 0;
+    int link_ctas = 64;            // CTAs (= SMs) given to a link-bound store phase in the overlapped schedule (NSB200_LINK_CTAS)
     bool u_in_window = false;      // resident state known to vanish outside the cube |k|_inf <= kmax
     // the RK kernel leaves w = i k x (next input) in the curl buffer: valid for this input / row stride / window mode
     const cplx* curl_of = nullptr; int curl_rs = 0; bool curl_win = false;
@@ -177,8 +178,8 @@ struct nsb200_ctx {
     int* bar_dev = nullptr;
     unsigned* flags = nullptr;                     // barrier flag page at the end of the slab (peer mapped with it)
     unsigned epoch[NSB_BARRIER_SLOTS] = {0};
-    bool overlap = false;                          // two-stream schedule of the fused exchange (NSB200_OVERLAP=1 enables;
-                                                   // measured no gain: the link-bound kernel holds every SM slot)
+    bool overlap = false;                          // two-stream schedule of the fused exchange: on for >= 4 ranks, where it was
+                                                   // measured faster (NSB200_OVERLAP=0/1 overrides); needs link_ctas > 0 to pay
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     int sm_count = 0;
     int zgrid[3] = {0, 0, 0};
@@ -344,7 +345,10 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
     TmaMaps maps;
     const TmaMaps* mp = nullptr;
     const bool natural_in = (a.in_shift == 30) && (a.in_s1 == 0);
-    const bool pipe = h->use_pipe && h->use_tma && natural_in && h->ops->strided_pipe != nullptr;
+    // the persistent kernel also serves the overlapped multi-GPU schedule: a link-bound store phase runs on a
+    // restricted grid (link_ctas SMs) so that the other stream's HBM-bound pass gets the rest of the GPU
+    const bool link_limited = ps.p2p_out && h->overlap && h->link_ctas > 0;
+    const bool pipe = (h->use_pipe || link_limited) && h->use_tma && natural_in && h->ops->strided_pipe != nullptr;
     if (h->use_tma && natural_in && (h->ops->strided_T == 8 || pipe)) {
         memset(&maps, 0, sizeof maps);
         const int bc = pipe ? h->ops->pipe_T : 8;
@@ -362,7 +366,7 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         const double in_cnt = ps.in_w ? 2 * K + 1 : N, out_cnt = ps.out_w ? 2 * K + 1 : N;
         const double bytes = 16.0 * field_cnt * (double)n_outer * ps.nzv * (in_cnt + out_cnt);
         ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD), bytes, st);
-        if (pipe) CKI(h->ops->strided_pipe(ps.dir, &a, mp, n_outer, field_cnt, h->pipe_ctas, st));
+        if (pipe) CKI(h->ops->strided_pipe(ps.dir, &a, mp, n_outer, field_cnt, link_limited ? h->link_ctas : h->pipe_ctas, st));
         else CKI(h->ops->strided(ps.dir, &a, mp, n_outer, field_cnt, st));
     }
     h->launches++;
@@ -734,6 +738,8 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     { const char* e = getenv("NSB200_NO_TMA"); h->use_tma = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_NO_FUSE_CURL"); h->fuse_curl = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_PIPE"); h->use_pipe = (e && e[0] == '1'); }
+    h->link_ctas = (h->nranks >= 8) ? 128 : 96;   // measured: 4 ranks 11.22 -> 10.58 ms (96), 8 ranks 6.26 -> 6.02 ms (128)
+    { const char* e = getenv("NSB200_LINK_CTAS"); if (e) h->link_ctas = atoi(e); }
     h->ops = ops;
     h->field_elems = (size_t)h->nx_loc * h->N * h->nzp;
 #define CKC(call)                                                                                    \
@@ -760,7 +766,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     CKC(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_c, cudaEventDisableTiming));
-    { const char* e = getenv("NSB200_OVERLAP"); h->overlap = (e && e[0] == '1'); }
+    { const char* e = getenv("NSB200_OVERLAP"); h->overlap = e ? (e[0] == '1') : (h->nranks >= 4); }
     for (int i = 0; i < 6; ++i) {
         cudaEvent_t e;
         CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_field.push_back(e);
