@@ -766,7 +766,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     CKC(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_c, cudaEventDisableTiming));
-    { const char* e = getenv("NSB200_OVERLAP"); h->overlap = e ? (e[0] == '1') : (h->nranks >= 4); }
+    { const char* e = getenv("NSB200_OVERLAP"); h->overlap = e ? (e[0] == '1') : (h->nranks >= 4 && ops->strided_pipe != nullptr); }   // without the restricted-grid kernel (N != 512) the two-stream schedule was measured slower
     for (int i = 0; i < 6; ++i) {
         cudaEvent_t e;
         CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_field.push_back(e);
