@@ -238,14 +238,6 @@ struct ProfScope {
 };
 
 // ------------------------------------------------------------------------------ transform plumbing
-// One strided c2c pass.  axis 'y': Fourier slab [kx_loc][ky][kz], outer = kx_loc.  axis 'x': after the slab
-// exchange [kx][y_loc][kz], outer = y_loc.  `exch` selects the all-to-all block layout on the output
-// ('o', inverse y pass) or input ('i', forward y pass) side: element n of the transformed axis lives
-// at (n / ny_loc) * block + (n % ny_loc) * rs, i.e. one contiguous block per destination rank.
-// Windows (exact, see DESIGN.md "dealias support pruning"): `in_w` = the input is known to vanish for
-// transformed-axis wavenumbers |k| > kmax (not loaded); `out_w` = outputs with |k| > kmax are not stored
-// (the dealias mask zeroes them); `outer_w` = pencils whose outer wavenumber is > kmax are skipped;
-// nzv = number of kz columns carried.
 // Block layout of the slab all-to-all (pure host logic, exported as nsb200_exchange_layout so the CPU
 // tests can drive it): element (i_local, n, kz) of a y pencil, n being the y index, lives at
 //   (n >> shift) * block + i_local * outer + (n & mask) * rs + kz
@@ -257,6 +249,14 @@ static void exchange_layout(long N, int n_ranks, long rs, long out[5]) {
     out[0] = sh; out[1] = ny_loc - 1; out[2] = nx_loc * ny_loc * rs; out[3] = ny_loc * rs; out[4] = rs;
 }
 
+// One strided c2c pass.  axis 'y': Fourier slab [kx_loc][ky][kz], outer = kx_loc.  axis 'x': after the slab
+// exchange [kx][y_loc][kz], outer = y_loc.  `exch` selects the all-to-all block layout on the output
+// ('o', inverse y pass) or input ('i', forward y pass) side: element n of the transformed axis lives
+// at (n / ny_loc) * block + (n % ny_loc) * rs, i.e. one contiguous block per destination rank.
+// Windows (exact, see DESIGN.md "dealias support pruning"): `in_w` = the input is known to vanish for
+// transformed-axis wavenumbers |k| > kmax (not loaded); `out_w` = outputs with |k| > kmax are not stored
+// (the dealias mask zeroes them); `outer_w` = pencils whose outer wavenumber is > kmax are skipped;
+// nzv = number of kz columns carried.
 struct PassSpec {
     char axis; int dir; char exch;
     int in_rs, out_rs;       // row strides (complex elements) of source / destination
@@ -283,8 +283,6 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
             // global index of local plane i: x0 + i*xs ; first i above K, first i at or above N-K
             int lo, hi;
             h->plane_window(lo, hi);
-            lo = lo < 0 ? 0 : (lo > h->nx_loc ? h->nx_loc : lo);
-            hi = hi < 0 ? 0 : (hi > h->nx_loc ? h->nx_loc : hi);
             if (hi > lo) { a.outer_lo = lo; a.outer_hi = hi; n_outer -= hi - lo; }
         }
         a.in_so = (long long)N * ps.in_rs;  a.in_s2 = ps.in_rs;
@@ -438,8 +436,9 @@ static int gpu_barrier(nsb200_ctx* h, cudaStream_t st = nullptr, int slot = 0) {
 // NonlinearRHSBatch up to (not including) normalise/project/dealias: raw (u x w)^ of `in` left in R[0..2]
 // (row stride returned in *c_rs).  solver.c:637-683.  in_w: `in` is known to vanish outside the dealias
 // cube, so the inverse transforms skip those modes.  The forward transforms skip the modes the dealias
-// mask will zero whenever dealiasing is on.  Multi-rank: per-field pipelining of y pass -> all-to-all ->
-// x pass over two streams.
+// mask will zero whenever dealiasing is on.  Multi-rank: the exchange is fused into the store phase of the y /
+// forward-x pass over peer memory (optionally on two streams); the NCCL fallback pipelines
+// y pass -> all-to-all -> x pass per field.
 static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx*** c_out) {
     const bool out_w = h->prune && h->dealias == NSB200_DEALIAS_23;
     in_w = in_w && h->prune;
