@@ -8,6 +8,13 @@
 #define NSB_CAT(a, b) NSB_CAT2(a, b)
 #define NSB_FN(name) NSB_CAT(name, NSB_N)
 
+// the warp-per-transform fused z kernel exists for the 8 x 8 x 8 plan (64 butterflies per pass)
+#if NSB_N == 512
+#define NSB_HAVE_ZFW 1
+#else
+#define NSB_HAVE_ZFW 0
+#endif
+
 namespace {
 typedef BigPlan<NSB_N>::type BP;
 typedef ZPlan<NSB_N>::type ZP;
@@ -34,6 +41,10 @@ int setup() {
     e = cudaFuncSetAttribute(k_z_r2c<ZP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_z_fused<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZFusedSmem);
+    if (e != cudaSuccess) return (int)e;
+#if NSB_HAVE_ZFW
+    e = cudaFuncSetAttribute(k_z_fused_w<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpCfg<ZF>::SMEM);
+#endif
     return (int)e;
 }
 
@@ -96,6 +107,9 @@ int zlaunch(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s) 
     constexpr int TH = ZCfg<ZP>::THREADS;
     if (which == NSB_Z_C2R) k_z_c2r<ZP><<<dim3(grid_x, nfields), TH, kZSmem, s>>>(*a);
     else if (which == NSB_Z_R2C) k_z_r2c<ZP><<<dim3(grid_x, nfields), TH, kZSmem, s>>>(*a);
+#if NSB_HAVE_ZFW
+    else if (which == NSB_Z_FUSED_W) k_z_fused_w<ZF><<<dim3(grid_x), ZWarpCfg<ZF>::THREADS, ZWarpCfg<ZF>::SMEM, s>>>(*a);
+#endif
     else k_z_fused<ZF><<<dim3(grid_x), ZFusedCfg<ZF>::THREADS, kZFusedSmem, s>>>(*a);
     return (int)cudaGetLastError();
 }
@@ -105,9 +119,12 @@ int zocc(int which) {
     constexpr int TH = ZCfg<ZP>::THREADS;
     if (which == NSB_Z_C2R) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_c2r<ZP>, TH, kZSmem);
     else if (which == NSB_Z_R2C) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_r2c<ZP>, TH, kZSmem);
+#if NSB_HAVE_ZFW
+    else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused_w<ZF>, ZWarpCfg<ZF>::THREADS, ZWarpCfg<ZF>::SMEM);
+#endif
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused<ZF>, ZFusedCfg<ZF>::THREADS, kZFusedSmem);
     return n;
 }
 }  // namespace
 
-extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, NSB_PIPE_TCOLS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC};
+extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, NSB_PIPE_TCOLS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G, NSB_HAVE_ZFW}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC};

@@ -589,6 +589,217 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
     }
 }
 
+// ------------------------------------------------------------------------------ fused z kernel, one warp per transform
+// Second generation of the fused z kernel (N = 512: plan 8 x 8 x 8, 64 butterflies per pass).  A pencil pair is
+// owned by a 3-warp CTA; every transform is run by ONE warp, lane L owning the Hermitian-mirrored butterfly pair
+// (b, b') = (L, 64 - L) (lane 0: the two self-mirrored butterflies 0 and 32) in the first and last pass:
+//   * butterflies b and b' of the inverse pass 1 consume the SAME half-spectrum entries (k and N - k), so every
+//     entry is loaded once (the first generation loaded it in two threads);
+//   * outputs Z(k) and Z(N - k) of the forward last pass meet in one lane: the r2c unpack needs no exchange;
+//   * pass-1 twiddles of b' are conj(W^{b k1}) * W_8^{k1}; the W_8 factor is a cyclic shift of the butterfly
+//     inputs (DFT shift theorem), so one register set serves both butterflies;
+//   * the passes of a transform synchronise with __syncwarp(); only two CTA barriers per pencil pair remain
+//     (real-space fields complete / real-space fields consumed), against eight before.
+// Warp t inverse-transforms u_{t+1} and w_{t+2}, forms component t of u x w at its own points and transforms it
+// forward in the buffer of u_{t+1}.
+template <class P> struct ZWarpCfg {
+    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && P::M1 == 64, "warp-per-transform kernel: plan 8 x R2 x 8 with 64 butterflies per pass");
+    static_assert(P::NB2 % 32 == 0 && 32 % P::M2 == 0, "pass 2 must split evenly over the warp with one twiddle set per lane");
+    static constexpr int THREADS = 96;
+    static constexpr int SMEM = 6 * P::NPAD * 16;
+#ifndef NSB_ZFW_MINB
+#define NSB_ZFW_MINB 4
+#endif
+    static constexpr int MINB = NSB_ZFW_MINB;
+};
+
+NSB_HD cplx zw_pack(cplx A, cplx B) { return mk(A.x - B.y, A.y + B.x); }     // element n <= N/2 : A + i B
+NSB_HD cplx zw_packc(cplx A, cplx B) { return mk(A.x + B.y, B.x - A.y); }    // element N - n   : conj(A) + i conj(B)
+
+// the mirrored butterfly pair of lane L (self: both butterflies are their own mirror images)
+template <class P> NSB_HD void zw_lane_pair(int L, int& bA, int& bB, bool& self) {
+    self = (L == 0);
+    bA = L;
+    bB = self ? P::M1 / 2 : P::M1 - L;
+}
+// pass-1 twiddle registers of the lane: W^{bA k1}; the self pair keeps W^{(M1/2) k1} (butterfly 0 needs none)
+template <class P> NSB_HD void zw_load_tw1(int L, const cplx* __restrict__ tw, cplx* w) {
+    const int b = L ? L : P::M1 / 2;
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1) w[k1 - 1] = tw[b * k1];
+}
+// radix-8 pass-1 butterflies of the pair on values in registers: xa (inputs of bA, natural order) and xb (inputs
+// of bB) are replaced by the twiddled outputs, ready for the scatter to row k1
+template <int DIR> NSB_HD void zw_bfly_pair(bool self, cplx* xa, cplx* xb, const cplx* w) {
+    Dft<8, DIR>::run(xa);
+    if (!self) {
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) xa[k1] = cmul_dir<DIR>(xa[k1], w[k1 - 1]);
+    }
+    cplx y[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) y[n] = xb[(n + 7) & 7];       // shift by one: outputs pick up W_8^{k1} (conjugated for INV)
+    Dft<8, DIR>::run(y);
+    xb[0] = y[0];
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1) xb[k1] = cmul_dir<-DIR>(y[k1], w[k1 - 1]);
+}
+template <class P> NSB_HD void zw_scatter_pair(int bA, int bB, cplx* buf, const cplx* xa, const cplx* xb) {
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) buf[k1 * P::ROW + bA] = xa[k1];
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) buf[k1 * P::ROW + bB] = xb[k1];
+}
+// inverse pass 1 of one transform: ld(k, A, B) returns the half-spectrum entries of the two packed pencils
+template <class P, class Ld> NSB_HD void zw_inv_pass1(int L, cplx* buf, const cplx* w, Ld ld) {
+    constexpr int M1 = P::M1;
+    int bA, bB; bool self;
+    zw_lane_pair<P>(L, bA, bB, self);
+    cplx xa[8], xb[8];
+    if (!self) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cplx A, B;
+            ld(bA + j * M1, A, B);
+            xa[j] = zw_pack(A, B); xb[7 - j] = zw_packc(A, B);
+            ld(bB + j * M1, A, B);
+            xb[j] = zw_pack(A, B); xa[7 - j] = zw_packc(A, B);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j <= 4; ++j) {                        // butterfly 0: n = j M1, mirror of j is 8 - j
+            cplx A, B;
+            ld(j * M1, A, B);
+            if (j == 0 || j == 4) { A.y = 0.0; B.y = 0.0; }   // like FFTW's c2r: imaginary parts of k = 0, N/2 are ignored
+            xa[j] = zw_pack(A, B);
+            if (j >= 1 && j <= 3) xa[8 - j] = zw_packc(A, B);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                         // butterfly M1/2 is its own mirror image
+            cplx A, B;
+            ld(M1 / 2 + j * M1, A, B);
+            xb[j] = zw_pack(A, B); xb[7 - j] = zw_packc(A, B);
+        }
+    }
+    zw_bfly_pair<INV>(self, xa, xb, w);
+    zw_scatter_pair<P>(bA, bB, buf, xa, xb);
+}
+// last pass of the pair, outputs in registers: va[j] = X(bA + j M1), vb[j] = X(bB + j M1)
+template <class P, int DIR> NSB_HD void zw_last_pair(int L, const cplx* buf, cplx* va, cplx* vb) {
+    int bA, bB; bool self;
+    zw_lane_pair<P>(L, bA, bB, self);
+    fft_pass_last<P, DIR, 1>(bA, buf, va);
+    fft_pass_last<P, DIR, 1>(bB, buf, vb);
+}
+// r2c unpack of the forward result: st(k, A, B) stores the half-spectrum entries of the two pencils
+template <class P, class St> NSB_HD void zw_unpack_store(int L, const cplx* va, const cplx* vb, St st) {
+    constexpr int M1 = P::M1;
+    int bA, bB; bool self;
+    zw_lane_pair<P>(L, bA, bB, self);
+    if (!self) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cplx A, B;
+            unpack_pair(va[j], vb[7 - j], A, B);
+            st(bA + j * M1, A, B);
+            unpack_pair(vb[j], va[7 - j], A, B);
+            st(bB + j * M1, A, B);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j <= 4; ++j) {
+            cplx A, B;
+            unpack_pair(va[j], va[(8 - j) & 7], A, B);
+            st(j * M1, A, B);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cplx A, B;
+            unpack_pair(vb[j], vb[7 - j], A, B);
+            st(M1 / 2 + j * M1, A, B);
+        }
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_fused_w(const ZArgs a) {
+    constexpr int NP = P::NPAD;
+    extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
+    cplx* sm = reinterpret_cast<cplx*>(nsb_smem_raw);
+    const int t = threadIdx.x >> 5;          // warp = output component
+    const int L = threadIdx.x & 31;
+    const cplx* __restrict__ tw = a.tw;
+    const int kzin = a.kz_in, kzout = a.kz_out;
+    const int i1 = (t + 1) % 3, i2 = (t + 2) % 3;
+    const int fu = i1, fw = 3 + i2;          // the two fields this warp brings to real space
+    int bA, bB; bool self;
+    zw_lane_pair<P>(L, bA, bB, self);
+    const int rbA = fft_row_base<P>(bA), rbB = fft_row_base<P>(bB);
+    cplx w1[7], w2[P::R2 - 1];
+    zw_load_tw1<P>(L, tw, w1);
+    load_tw_pass2<P>(L, tw, w2);
+    for (long long pr = blockIdx.x; pr < a.npairs; pr += gridDim.x) {
+        const long long roff = 2 * pr * a.rs;
+#if defined(__CUDA_ARCH__) && defined(NSB_ZFW_PREFETCH)
+        // pull the next pair of this CTA into L2 while this one is transformed (12 rows of kz_in entries)
+        if (pr + gridDim.x < a.npairs) {
+            const long long nroff = 2 * (pr + gridDim.x) * a.rs;
+            const int lines = (kzin * 16 + 127) / 128;
+            for (int i = threadIdx.x; i < 12 * lines; i += 96) {
+                const int row = i / lines, ln = i % lines;
+                const cplx* p = a.base + (row >> 1) * a.fstride + nroff + (row & 1) * a.rs + ln * 8;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        }
+#endif
+        cplx ca[8], cb[8];
+#pragma unroll
+        for (int ff = 0; ff < 2; ++ff) {
+            const int f = ff ? fw : fu;
+            cplx* buf = sm + f * NP;
+            const cplx* ra = a.base + f * a.fstride + roff;
+            const cplx* rb = ra + a.rs;
+            zw_inv_pass1<P>(L, buf, w1, [&](int k, cplx& A, cplx& B) {
+                if (k < kzin) { A = NSB_LDCG(ra + k); B = NSB_LDCG(rb + k); }
+                else { A = mk(0.0, 0.0); B = mk(0.0, 0.0); }
+            });
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_rw<P, INV, 1>(L + 32 * i, buf, w2);
+            __syncwarp();
+            zw_last_pair<P, INV>(L, buf, ca, cb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { buf[rbA + j] = ca[j]; buf[rbB + j] = cb[j]; }   // in place (the lane's own rows): point bA + j M1 lives at rbA + j
+        }
+        __syncthreads();                                   // the six real-space fields of the pair are complete
+        {
+            // component t = u_{i1} w_{i2} - u_{i2} w_{i1}; w_{i2} at this lane's points is still in registers (ca, cb)
+            const cplx* u1 = sm + i1 * NP;
+            const cplx* u2 = sm + i2 * NP;
+            const cplx* v1 = sm + (3 + i1) * NP;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ca[j] = cross_comp(u1[rbA + j], ca[j], u2[rbA + j], v1[rbA + j]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cb[j] = cross_comp(u1[rbB + j], cb[j], u2[rbB + j], v1[rbB + j]);
+        }
+        zw_bfly_pair<FWD>(self, ca, cb, w1);
+        __syncthreads();                                   // all reads of the real-space fields are done
+        cplx* buf = sm + fu * NP;
+        zw_scatter_pair<P>(bA, bB, buf, ca, cb);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_rw<P, FWD, 1>(L + 32 * i, buf, w2);
+        __syncwarp();
+        zw_last_pair<P, FWD>(L, buf, ca, cb);
+        cplx* oa = a.base + t * a.fstride + roff;
+        cplx* ob = oa + a.rs;
+        zw_unpack_store<P>(L, ca, cb, [&](int k, cplx A, cplx B) {
+            if (k < kzout) { oa[k] = A; ob[k] = B; }
+        });
+        __syncwarp();                                      // the buffer is free for the next pair's inverse pass 1
+    }
+}
+
 // ------------------------------------------------------------------------------ launch helpers
 #ifndef NSB_STRIDED_TP_1024
 #define NSB_STRIDED_TP_1024 64

@@ -182,7 +182,8 @@ struct nsb200_ctx {
                                                    // measured faster (NSB200_OVERLAP=0/1 overrides); needs link_ctas > 0 to pay
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     int sm_count = 0;
-    int zgrid[3] = {0, 0, 0};
+    int zgrid[NSB_Z_KINDS] = {0, 0, 0, 0};
+    int zf_kind = NSB_Z_FUSED;     // NSB_Z_FUSED_W (one warp per transform) where built; NSB200_ZF=old keeps the first generation
     long launches = 0;
     size_t bytes = 0;
     bool prof_on = false;
@@ -386,15 +387,17 @@ static int run_z(nsb200_ctx* h, int which, int nfields, cplx* const* f, int rs, 
     a.npairs = (long long)h->N * h->ny_loc / 2;
     a.kz_in = kz_in;
     a.kz_out = kz_out;
+    const bool fused = (which == NSB_Z_FUSED);
+    if (fused) which = h->zf_kind;
     const int gpc = h->ops->z_pairs_per_cta[which];
     long long want = (a.npairs + gpc - 1) / gpc;
     int grid = (int)(want < h->zgrid[which] ? want : h->zgrid[which]);
     {
         const double rows = 2.0 * (double)a.npairs;
-        const double bytes = which == NSB_Z_FUSED ? rows * 16.0 * (6.0 * kz_in + 3.0 * kz_out)
+        const double bytes = fused ? rows * 16.0 * (6.0 * kz_in + 3.0 * kz_out)
                            : which == NSB_Z_C2R ? nfields * rows * (16.0 * kz_in + 8.0 * h->N)
                                                 : nfields * rows * (8.0 * h->N + 16.0 * kz_out);
-        ProfScope ps(h, which == NSB_Z_FUSED ? NSB200_PC_Z_FUSED : which == NSB_Z_C2R ? NSB200_PC_Z_C2R : NSB200_PC_Z_R2C, bytes);
+        ProfScope ps(h, fused ? NSB200_PC_Z_FUSED : which == NSB_Z_C2R ? NSB200_PC_Z_C2R : NSB200_PC_Z_R2C, bytes);
         CKI(h->ops->z(which, &a, nfields, grid, h->stream));
     }
     h->launches++;
@@ -740,6 +743,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     h->link_ctas = (h->nranks >= 8) ? 128 : 96;   // measured: 4 ranks 11.22 -> 10.58 ms (96), 8 ranks 6.26 -> 6.02 ms (128)
     { const char* e = getenv("NSB200_LINK_CTAS"); if (e) h->link_ctas = atoi(e); }
     h->ops = ops;
+    { const char* e = getenv("NSB200_ZF"); if (ops->z_pairs_per_cta[NSB_Z_FUSED_W] > 0 && !(e && !strcmp(e, "old"))) h->zf_kind = NSB_Z_FUSED_W; }
     h->field_elems = (size_t)h->nx_loc * h->N * h->nzp;
 #define CKC(call)                                                                                    \
     do {                                                                                             \
@@ -807,7 +811,8 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
         int e = ops->setup();
         if (e != 0) { fail(std::string("kernel attribute setup failed: ") + cudaGetErrorString((cudaError_t)e)); nsb200_destroy(h); return 1; }
         if (ops->pipe_occupancy) { int occ = ops->pipe_occupancy(); h->pipe_ctas = (occ > 0 ? occ : 1) * h->sm_count; }
-        for (int w = 0; w < 3; ++w) {
+        for (int w = 0; w < NSB_Z_KINDS; ++w) {
+            if (ops->z_pairs_per_cta[w] == 0) continue;   // not built for this N
             int occ = ops->z_occupancy(w);
             if (occ < 1) { fail("z kernel does not fit on an SM"); nsb200_destroy(h); return 1; }
             h->zgrid[w] = occ * h->sm_count;

@@ -209,6 +209,101 @@ template <class P> int check_fused() {
     return err / nrm < 1e-13 ? 0 : 1;
 }
 
+// Emulates k_z_fused_w (one warp per transform, mirrored butterfly pairs per lane) for one pencil pair with the
+// kernel's own lane helpers, and checks it against the straightforward formulation.
+template <class P> int check_fused_warp() {
+    constexpr int N = P::N, NP = P::NPAD;
+    std::vector<cplx> tw(N), sm(6 * NP, mk(1e300, 1e300));
+    for (int m = 0; m < N; ++m) {
+        long double a = -2.0L * 3.14159265358979323846264338327950288L * m / N;
+        tw[m] = mk((double)cosl(a), (double)sinl(a));
+    }
+    std::vector<cplx> rows[6][2], outA[3], outB[3];
+    for (int f = 0; f < 6; ++f) for (int r = 0; r < 2; ++r) { rows[f][r].resize(N / 2 + 1); for (auto& z : rows[f][r]) z = mk(frand(), frand()); }
+    for (int t = 0; t < 3; ++t) { outA[t].assign(N / 2 + 1, mk(1e300, 1e300)); outB[t].assign(N / 2 + 1, mk(1e300, 1e300)); }
+    // inverse transforms, warp t: fields (t+1)%3 and 3 + (t+2)%3
+    for (int t = 0; t < 3; ++t) for (int ff = 0; ff < 2; ++ff) {
+        const int f = ff ? 3 + (t + 2) % 3 : (t + 1) % 3;
+        cplx* buf = sm.data() + f * NP;
+        for (int L = 0; L < 32; ++L) {
+            cplx w1[7]; zw_load_tw1<P>(L, tw.data(), w1);
+            zw_inv_pass1<P>(L, buf, w1, [&](int k, cplx& A, cplx& B) { A = rows[f][0][k]; B = rows[f][1][k]; });
+        }
+        for (int L = 0; L < 32; ++L) {
+            cplx w2[P::R2 - 1]; load_tw_pass2<P>(L, tw.data(), w2);
+            for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_rw<P, INV, 1>(L + 32 * i, buf, w2);
+        }
+        std::vector<cplx> keep(32 * 16);
+        for (int L = 0; L < 32; ++L) zw_last_pair<P, INV>(L, buf, &keep[L * 16], &keep[L * 16 + 8]);
+        for (int L = 0; L < 32; ++L) {
+            int bA, bB; bool self; zw_lane_pair<P>(L, bA, bB, self);
+            for (int j = 0; j < 8; ++j) { buf[fft_row_base<P>(bA) + j] = keep[L * 16 + j]; buf[fft_row_base<P>(bB) + j] = keep[L * 16 + 8 + j]; }
+        }
+    }
+    std::vector<double> real[6][2];
+    for (int f = 0; f < 6; ++f) for (int r = 0; r < 2; ++r) {
+        real[f][r].resize(N);
+        for (int n = 0; n < N; ++n) {
+            long double sacc = 0;
+            for (int k = 0; k < N; ++k) {
+                int kk = k <= N / 2 ? k : N - k;
+                long double ar = rows[f][r][kk].x, ai = (k <= N / 2 ? rows[f][r][kk].y : -rows[f][r][kk].y);
+                if (k == 0 || k == N / 2) ai = 0;
+                long double a = 2.0L * 3.14159265358979323846264338327950288L * ((long long)n * k % N) / N;
+                sacc += ar * cosl(a) - ai * sinl(a);
+            }
+            real[f][r][n] = (double)sacc;
+        }
+    }
+    // cross product + forward pass 1 in registers (before the second barrier), then scatter
+    std::vector<cplx> creg(3 * 32 * 16);
+    for (int t = 0; t < 3; ++t) for (int L = 0; L < 32; ++L) {
+        int bA, bB; bool self; zw_lane_pair<P>(L, bA, bB, self);
+        const int i1 = (t + 1) % 3, i2 = (t + 2) % 3, rbA = fft_row_base<P>(bA), rbB = fft_row_base<P>(bB);
+        cplx* ca = &creg[(t * 32 + L) * 16]; cplx* cb = ca + 8;
+        for (int j = 0; j < 8; ++j) {
+            ca[j] = cross_comp(sm[i1 * NP + rbA + j], sm[(3 + i2) * NP + rbA + j], sm[i2 * NP + rbA + j], sm[(3 + i1) * NP + rbA + j]);
+            cb[j] = cross_comp(sm[i1 * NP + rbB + j], sm[(3 + i2) * NP + rbB + j], sm[i2 * NP + rbB + j], sm[(3 + i1) * NP + rbB + j]);
+        }
+        cplx w1[7]; zw_load_tw1<P>(L, tw.data(), w1);
+        zw_bfly_pair<FWD>(self, ca, cb, w1);
+    }
+    for (int t = 0; t < 3; ++t) {
+        cplx* buf = sm.data() + ((t + 1) % 3) * NP;
+        for (int L = 0; L < 32; ++L) {
+            int bA, bB; bool self; zw_lane_pair<P>(L, bA, bB, self);
+            zw_scatter_pair<P>(bA, bB, buf, &creg[(t * 32 + L) * 16], &creg[(t * 32 + L) * 16 + 8]);
+        }
+        for (int L = 0; L < 32; ++L) {
+            cplx w2[P::R2 - 1]; load_tw_pass2<P>(L, tw.data(), w2);
+            for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_rw<P, FWD, 1>(L + 32 * i, buf, w2);
+        }
+        for (int L = 0; L < 32; ++L) {
+            cplx va[8], vb[8];
+            zw_last_pair<P, FWD>(L, buf, va, vb);
+            zw_unpack_store<P>(L, va, vb, [&](int k, cplx A, cplx B) { outA[t][k] = A; outB[t][k] = B; });
+        }
+    }
+    double err = 0, nrm = 0;
+    for (int t = 0; t < 3; ++t) for (int r = 0; r < 2; ++r) {
+        int i1 = (t + 1) % 3, i2 = (t + 2) % 3;
+        std::vector<double> c(N);
+        for (int n = 0; n < N; ++n) c[n] = real[i1][r][n] * real[3 + i2][r][n] - real[i2][r][n] * real[3 + i1][r][n];
+        for (int k = 0; k <= N / 2; ++k) {
+            long double sr = 0, si = 0;
+            for (int n = 0; n < N; ++n) {
+                long double a = -2.0L * 3.14159265358979323846264338327950288L * ((long long)n * k % N) / N;
+                sr += c[n] * cosl(a); si += c[n] * sinl(a);
+            }
+            cplx got = r == 0 ? outA[t][k] : outB[t][k];
+            err = fmax(err, fmax(fabs(got.x - (double)sr), fabs(got.y - (double)si)));
+            nrm = fmax(nrm, fmax(fabs((double)sr), fabs((double)si)));
+        }
+    }
+    printf("fused (warp per transform) N=%d (%d,%d,%d): max rel err %.3e\n", N, P::R1, P::R2, P::R3, err / nrm);
+    return err / nrm < 1e-13 ? 0 : 1;
+}
+
 int main() {
     int bad = 0;
     bad += check<BigPlan<16>::type>("big");
@@ -236,6 +331,7 @@ int main() {
     bad += check<FftPlan<256, 4, 4, 4, 1, 4>>("zf4");
     bad += check_fused<FftPlan<256, 4, 4, 4, 1, 4>>();
     bad += check_fused<ZFPlan<1024>::type>();
+    bad += check_fused_warp<ZFPlan<512>::type>();
     bad += check_pack<16>();
     bad += check_pack<64>();
     bad += check_pack<512>();

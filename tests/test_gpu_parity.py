@@ -319,7 +319,7 @@ def test_against_reference_build_64():
 
 
 # ----------------------------------------------------------------------------- BASELINE sizes: size-independent properties
-@pytest.mark.parametrize("n", [256, 512] + ([1024] if os.environ.get("NSB200_TEST_1024") == "1" else []))
+@pytest.mark.parametrize("n", [256, 512, 1024])   # 1024^3: 15 fields = 131 GB, fits one B200
 def test_large_grid_properties(n):
     nu, dt = 1e-3, 1e-3
     with nsb.Solver(n, nu=nu) as s:

@@ -44,3 +44,23 @@ def test_whole_program_series():
     assert ser.shape[0] == ref.shape[0] == 11 and int(g["n_writes"]) == 10
     assert np.allclose(ser[:, [0, 6, 7, 8, 5]], ref[:, [0, 1, 2, 3, 5]], rtol=1e-12, atol=0)
     assert rel(uf, g["u_final"]) < 1e-13
+
+
+def test_bench_workload_digest_128():
+    """bench.py's workload (RANDOM_PHASE seed 123456789, kp 4) at 128^3: restatement vs the digest the reference's own C
+    produced (tests/golden/make_golden_512.py 128).  The 512^3 digest of the same script is checked on the GPU."""
+    import sys
+    sys.path.insert(0, G)
+    from digest import plane_digest
+    g = np.load(os.path.join(G, "ref_rp128_digest.npz"))
+    n = int(g["n"]); N = (n, n, n)
+    idx = g["idx"]
+    u0 = o.random_phase_ic(N, seed=int(g["seed"]), kp=float(g["kp"]))
+    nl = o.nonlinear_rhs(u0, N)
+    u1 = o.rk4_step(u0, N, float(g["dt"]), float(g["nu"]))
+    for x, tag in ((u0, "u0"), (nl, "nl"), (u1, "u1")):
+        scale = float(g[tag + "_max"])
+        assert np.abs(x[idx[:, 0], idx[:, 1], idx[:, 2], :] - g[tag + "_s"]).max() < 1e-13 * scale
+        P, L1 = plane_digest(x)
+        assert np.abs(P - g[tag + "_p"]).max() < 1e-13 * scale * n
+        assert np.allclose(L1, g[tag + "_l1"], rtol=1e-11, atol=1e-13 * scale * n * n)
