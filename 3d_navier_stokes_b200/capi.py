@@ -23,6 +23,8 @@ SYMBOLS = [
     ("nsb200_local_fourier_elems", ctypes.c_long, [ctypes.c_void_p]),
     ("nsb200_upload_uhat", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     ("nsb200_download_uhat", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    ("nsb200_upload_uhat_window", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    ("nsb200_download_uhat_window", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     ("nsb200_rk4_step", ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
     ("nsb200_rk4_steps", ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int]),
     ("nsb200_nonlinear_rhs", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -43,11 +45,12 @@ SYMBOLS = [
     ("nsb200_profile_bytes", ctypes.c_int, [ctypes.c_void_p, _DP]),
     ("nsb200_launch_count", ctypes.c_long, [ctypes.c_void_p]),
     ("nsb200_device_bytes", ctypes.c_long, [ctypes.c_void_p]),
+    ("nsb200_link_bytes", ctypes.c_double, [ctypes.c_void_p]),
 ]
 
 PC_NAMES = ["curl", "y_inv", "x_inv", "z_fused", "x_fwd", "y_fwd", "rk", "z_c2r", "z_r2c"]
 PC_COUNT = 16
-OP_RK4_STEP, OP_FFT_C2R_R2C, OP_PASS_Y, OP_PASS_X, OP_PASS_Z, OP_L2_FLUSH, OP_Z_FUSED, OP_RK_POINTWISE = range(8)
+OP_RK4_STEP, OP_FFT_C2R_R2C, OP_PASS_Y, OP_PASS_X, OP_PASS_Z, OP_L2_FLUSH, OP_Z_FUSED, OP_RK_POINTWISE, OP_TILE_COPY_Y, OP_TILE_COPY_X = range(10)
 
 
 def lib_path():

@@ -329,6 +329,41 @@ NSB_HD void fft_pass2_rw(int b, cplx* sm, const cplx* w) {
     for (int kp = 0; kp < P::R2; ++kp) sm[(base + kp * P::M2) * STRIDE] = v[kp];
 }
 
+// radix-8 mid pass with the twiddle powers formed on the fly from W^1, W^2, W^4 of the butterfly (12 registers
+// instead of 28): w3 = w1 w2, w5 = w1 w4, w6 = w2 w4, w7 = w3 w4
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass2_r8_base(int b, cplx* sm, cplx wa, cplx wb, cplx wc) {
+    static_assert(P::PASSES >= 3 && P::R2 == 8, "radix-8 pass 2");
+    const int k1 = b / P::M2, m2 = b % P::M2;
+    const int base = k1 * P::ROW + m2;
+    cplx v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = sm[(base + j * P::M2) * STRIDE];
+    Dft<8, DIR>::run(v);
+    v[1] = cmul_dir<DIR>(v[1], wa);
+    v[2] = cmul_dir<DIR>(v[2], wb);
+    v[4] = cmul_dir<DIR>(v[4], wc);
+    const cplx w3 = cmul(wa, wb);
+    v[3] = cmul_dir<DIR>(v[3], w3);
+    v[7] = cmul_dir<DIR>(v[7], cmul(w3, wc));
+    v[5] = cmul_dir<DIR>(v[5], cmul(wa, wc));
+    v[6] = cmul_dir<DIR>(v[6], cmul(wb, wc));
+#pragma unroll
+    for (int kp = 0; kp < 8; ++kp) sm[(base + kp * P::M2) * STRIDE] = v[kp];
+}
+
+// v[k] *= W^k (DIR) for k = 1..7 with W^3, W^5, W^6, W^7 formed on the fly from W^1, W^2, W^4
+template <int DIR> NSB_HD void twiddle8_base(cplx* v, cplx wa, cplx wb, cplx wc) {
+    v[1] = cmul_dir<DIR>(v[1], wa);
+    v[2] = cmul_dir<DIR>(v[2], wb);
+    v[4] = cmul_dir<DIR>(v[4], wc);
+    const cplx w3 = cmul(wa, wb);
+    v[3] = cmul_dir<DIR>(v[3], w3);
+    v[7] = cmul_dir<DIR>(v[7], cmul(w3, wc));
+    v[5] = cmul_dir<DIR>(v[5], cmul(wa, wc));
+    v[6] = cmul_dir<DIR>(v[6], cmul(wb, wc));
+}
+
 // start of the RL contiguous elements the last pass of butterfly b works on (b = k1 + R1*k1' [+ R1*R2*k1''])
 template <class P> NSB_HD int fft_row_base(int b) {
     if constexpr (P::PASSES == 4) {

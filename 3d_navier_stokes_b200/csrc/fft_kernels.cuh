@@ -101,6 +101,7 @@ struct StridedArgs {
     int out_rank_lo;    // p2p: destination rank = n & out_mask, local index = n >> out_shift (cyclic kx planes)
                         //      instead of rank = n >> out_shift, local index = n & out_mask (contiguous y slabs)
     long long peer_delta[NSB_MAX_PEERS];
+    int copy_only;      // measurement: move the tile through shared memory without transforming it (the access-pattern ceiling)
 };
 
 template <class P, int T, int TP, int DIR, bool TMA>
@@ -145,6 +146,11 @@ __global__ void __launch_bounds__(T * TP) k_fft_strided(const StridedArgs a, con
             }
         }
         nsb_mbar_wait(bar, 0);
+        if (a.copy_only) {
+            if (valid)
+                for (int n = q; n < P::N; n += TP) dst[(long long)n * a.out_s2] = sm[n * T];
+            return;
+        }
         for (int b = q; b < P::NB1; b += TP) fft_pass1_inplace<P, DIR, T>(b, sm, tw);
         __syncthreads();
     } else
@@ -259,6 +265,11 @@ __global__ void __launch_bounds__(T * P::NB1, (T == 4) ? 3 : 1) k_fft_strided_pi
         }
     };
     if (threadIdx.x == 0 && t0 < t1) issue(t0, 0);
+    // one butterfly per thread and pass: its loop-invariant twiddles live in registers for the whole run of tiles
+    static_assert(P::NB1 == TP && (P::PASSES < 3 || P::NB2 == TP), "persistent strided pass: one butterfly per thread");
+    cplx w1[P::R1 - 1], w2[P::PASSES >= 3 ? P::R2 - 1 : 1];
+    load_tw_pass1<P>(q, tw, w1);
+    if constexpr (P::PASSES >= 3) load_tw_pass2<P>(q, tw, w2);
     const long long os1 = a.out_s1, os2 = a.out_s2;
     const int osh = a.out_shift, omk = a.out_mask, slo = a.out_skip_lo, shi = a.out_skip_hi;
     for (int t = t0; t < t1; ++t) {
@@ -273,10 +284,16 @@ __global__ void __launch_bounds__(T * P::NB1, (T == 4) ? 3 : 1) k_fft_strided_pi
         cplx* dst = a.dst[field] + ((long long)outer * a.out_so + kz);
         cplx* sm = smem + (size_t)buf * N * T + p;
         nsb_mbar_wait(bar0 + 8u * buf, (unsigned)((it >> 1) & 1));
-        for (int b = q; b < P::NB1; b += TP) fft_pass1_inplace<P, DIR, T>(b, sm, tw);
+        {
+            cplx v[P::R1];
+#pragma unroll
+            for (int j = 0; j < P::R1; ++j) v[j] = sm[(q + j * P::M1) * T];
+            fft_pass1_regs_rw<P, DIR>(v, w1);
+            fft_pass1_scatter<P, T>(q, sm, v);     // unpadded plan: in place (the thread's own column of the digit matrix)
+        }
         __syncthreads();
         if constexpr (P::PASSES == 3) {
-            for (int b = q; b < P::NB2; b += TP) fft_pass2<P, DIR, T>(b, sm, tw);
+            fft_pass2_rw<P, DIR, T>(q, sm, w2);
             __syncthreads();
         }
         for (int b = q; b < P::NBL; b += TP) {
@@ -798,6 +815,149 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
         });
         __syncwarp();                                      // the buffer is free for the next pair's inverse pass 1
     }
+}
+
+// Persistent strided pass, third generation (N = 512): ONE CTA per SM, two independent groups of 256 threads, a ring
+// of three 64 KB tile buffers fed by TMA.  Group g transforms the tiles it, it + 2, ... of the CTA's run; the tile
+// it + 3 is requested into a buffer as soon as the group that used it has read its last value, so one or two tiles
+// are always in flight while both groups compute.  The groups drift apart in phase, which is what overlaps the
+// shared-memory bound passes of one tile with the FP64 bound butterflies and the global stores of the other (the
+// single-group pipeline ran its 16 warps in lock step: 7 k cycles per tile against 6 k of HBM time).  Every thread
+// owns the Hermitian-mirrored butterfly pair (q, 64 - q) of pass 1, so one set of twiddle registers serves both
+// (see zw_bfly_pair), and the pass-2 butterflies q, q + 32 share theirs: no twiddle loads inside the tile loop.
+template <class P> struct RingCfg {
+    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && P::M1 == 64 && P::NB2 == 64 && P::ROW == P::M1,
+                  "ring kernel: unpadded 8 x 8 x 8 plan");
+    static constexpr int T = 8, GROUP = 256, NGROUP = 2, NBUF = 3;
+    static constexpr int THREADS = NGROUP * GROUP;
+    static constexpr size_t SMEM = (size_t)NBUF * P::N * T * sizeof(cplx);
+#ifndef NSB_RING_SHIFT
+#define NSB_RING_SHIFT 1
+#endif
+    static constexpr int SHIFT = NSB_RING_SHIFT;      // slots group 1 runs behind group 0
+};
+template <class P, int DIR>
+__global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring(const StridedArgs a, const __grid_constant__ TmaMaps maps, const PipeArgs pa) {
+    constexpr int T = RingCfg<P>::T, N = P::N, NBUF = RingCfg<P>::NBUF, GROUP = RingCfg<P>::GROUP, SHIFT = RingCfg<P>::SHIFT;
+    extern __shared__ __align__(1024) unsigned char nsb_smem_raw[];
+    cplx* smem = reinterpret_cast<cplx*>(nsb_smem_raw);
+    __shared__ __align__(8) unsigned long long s_bar[NBUF];
+    __shared__ long long s_delta[NSB_MAX_PEERS];
+    if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = a.peer_delta[threadIdx.x];
+    const int g = threadIdx.x / GROUP, tid = threadIdx.x % GROUP;
+    const int p = tid % T, q = tid / T;               // column of the tile, butterfly index 0..31
+    const cplx* __restrict__ tw = a.tw;
+#ifdef __CUDA_ARCH__
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NBUF; ++i) nsb_mbar_init(bar0 + 8u * i, 1);
+    }
+    __syncthreads();
+    const int t0 = blockIdx.x * pa.tiles_per_cta;
+    const int t1 = (t0 + pa.tiles_per_cta < pa.total_tiles) ? t0 + pa.tiles_per_cta : pa.total_tiles;
+    const int nt = t1 - t0;
+    auto issue = [&](int t, int buf) {
+        const int kzt = t % pa.nzt, rest = t / pa.nzt;
+        int outer = rest % pa.n_outer_eff;
+        const int field = rest / pa.n_outer_eff;
+        if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
+        constexpr int ROWS = TmaChunk<N>::ROWS, COUNT = TmaChunk<N>::COUNT;
+        const unsigned bar = bar0 + 8u * buf;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last touched through the generic proxy
+        nsb_mbar_expect_tx(bar, (unsigned)(N * T * sizeof(cplx)));
+#pragma unroll
+        for (int c = 0; c < COUNT; ++c) {
+            const bool use_hi = maps.pruned && (c >= COUNT / 2);
+            const void* mp = use_hi ? (const void*)&maps.hi[field] : (const void*)&maps.lo[field];
+            const int row = use_hi ? c * ROWS - maps.hi_row0 : c * ROWS;
+            nsb_tma_load_3d(sbase + (unsigned)((buf * N + c * ROWS) * T * sizeof(cplx)), mp, kzt * T * 2, row, outer, bar);
+        }
+    };
+    if (threadIdx.x == 0)
+        for (int i = 0; i < NBUF && i < nt; ++i) issue(t0 + i, i);
+    int bA, bB; bool self;
+    zw_lane_pair<P>(q, bA, bB, self);
+    // twiddles of the pair (see zw_load_tw1) and of the two pass-2 butterflies q, q + 32: the powers 1, 2, 4 stay in
+    // registers, the others are formed on the fly
+    const int tb = q ? q : P::M1 / 2;
+    const cplx w1a = tw[tb], w1b = tw[2 * tb], w1c = tw[4 * tb];
+    const cplx w2a = tw[P::R1 * (q % P::M2)], w2b = tw[P::R1 * (q % P::M2) * 2], w2c = tw[P::R1 * (q % P::M2) * 4];
+    const long long os1 = a.out_s1, os2 = a.out_s2;
+    const int osh = a.out_shift, omk = a.out_mask, slo = a.out_skip_lo, shi = a.out_skip_hi;
+    const int p2p = a.out_p2p, rank_lo = a.out_rank_lo;
+    // Time is cut into slots separated by CTA barriers; a group spends three consecutive slots on a tile (pass 1, pass 2,
+    // last pass + stores) and group 1 runs SHIFT slots behind group 0, so the two groups are always in different passes.
+    const int ntg = (nt - g + 1) / 2;                  // tiles of this group: it = g, g + 2, ...
+    const int nslots = 3 * ((nt + 1) / 2) + SHIFT;
+    int buf = 0;
+    bool valid = false;
+    cplx* dst = nullptr;
+    cplx* sm = smem;
+    for (int s = 0; s < nslots; ++s) {
+        const int ls = s - g * SHIFT;
+        const bool active = ls >= 0 && ls < 3 * ntg;
+        const int ph = active ? ls % 3 : -1;
+        const int it = g + 2 * (ls / 3);
+        if (ph == 0) {
+            const int t = t0 + it;
+            buf = it % NBUF;
+            const int kzt = t % pa.nzt, rest = t / pa.nzt;
+            int outer = rest % pa.n_outer_eff;
+            const int field = rest / pa.n_outer_eff;
+            if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
+            const int kz = kzt * T + p;
+            valid = kz < a.nzv;
+            dst = a.dst[field] + ((long long)outer * a.out_so + kz);
+            sm = smem + (size_t)buf * N * T + p;
+            nsb_mbar_wait(bar0 + 8u * buf, (unsigned)((it / NBUF) & 1));
+            {   // pass 1 in place: butterfly bA ...
+                cplx v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = sm[(bA + j * P::M1) * T];
+                Dft<8, DIR>::run(v);
+                if (!self) twiddle8_base<DIR>(v, w1a, w1b, w1c);
+#pragma unroll
+                for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + bA) * T] = v[k1];
+            }
+            {   // ... and its mirror image bB: inputs shifted by one, conjugated twiddles (zw_bfly_pair)
+                cplx y[8];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) y[n] = sm[(bB + ((n + 7) & 7) * P::M1) * T];
+                Dft<8, DIR>::run(y);
+                twiddle8_base<-DIR>(y, w1a, w1b, w1c);
+#pragma unroll
+                for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + bB) * T] = y[k1];
+            }
+        } else if (ph == 1) {
+            fft_pass2_r8_base<P, DIR, T>(q, sm, w2a, w2b, w2c);
+            fft_pass2_r8_base<P, DIR, T>(q + 32, sm, w2a, w2b, w2c);
+        } else if (ph == 2) {
+#pragma unroll 1
+            for (int b = q; b < P::NBL; b += 32) {
+                cplx v[P::RL];
+                fft_pass_last<P, DIR, T>(b, sm, v);
+                if (valid) {
+#pragma unroll
+                    for (int k2 = 0; k2 < P::RL; ++k2) {
+                        const int n = b + k2 * P::NBL;
+                        if (!(n >= slo && n < shi)) {
+                            if (p2p) {
+                                const int hi = n >> osh, lo = n & omk;
+                                cplx* d = reinterpret_cast<cplx*>(reinterpret_cast<char*>(dst) + s_delta[rank_lo ? lo : hi]);
+                                d[(long long)(rank_lo ? hi : lo) * os2] = v[k2];
+                            } else {
+                                dst[(long long)(n >> osh) * os1 + (long long)(n & omk) * os2] = v[k2];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (ph == 2 && tid == 0 && it + NBUF < nt) issue(t0 + it + NBUF, buf);   // every read of the buffer is done: refill it
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------ launch helpers

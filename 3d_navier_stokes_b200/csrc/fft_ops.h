@@ -22,6 +22,8 @@ struct FftOps {
     // persistent double-buffered strided pass (T = 4, TMA, natural input layout); NULL when not built for this N
     int (*strided_pipe)(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s);
     int (*pipe_occupancy)(void);
+    // persistent two-group ring pass (one CTA per SM, T = 8, TMA, natural input layout); NULL when not built for this N
+    int (*strided_ring)(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s);
 };
 
 const FftOps* nsb_get_fft_ops(int N);

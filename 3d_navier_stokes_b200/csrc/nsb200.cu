@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -146,7 +147,8 @@ struct nsb200_ctx {
     int nzc = 0;                   // compact row stride of the workspace when kz <= kmax only is carried
     bool prune = true;             // use the dealias support windows (NSB200_NO_PRUNE=1 disables)
     bool use_tma = true;           // TMA tile loads in the strided passes (NSB200_NO_TMA=1: cp.async path)
-    bool use_pipe = false;         // persistent double-buffered strided pass where built (NSB200_PIPE=1 enables; measured equal)
+    bool use_pipe = false;         // persistent double-buffered strided pass where built (NSB200_PIPE=1)
+    bool use_ring = true;          // persistent two-group ring pass where built (default; NSB200_RING=0 disables)
     int pipe_ctas = 0;
     int link_ctas = 64;            // CTAs (= SMs) given to a link-bound store phase in the overlapped schedule (NSB200_LINK_CTAS)
     bool u_in_window = false;      // resident state known to vanish outside the cube |k|_inf <= kmax
@@ -185,6 +187,7 @@ struct nsb200_ctx {
     int zgrid[NSB_Z_KINDS] = {0, 0, 0, 0};
     int zf_kind = NSB_Z_FUSED;     // NSB_Z_FUSED_W (one warp per transform) where built; NSB200_ZF=old keeps the first generation
     long launches = 0;
+    double link_bytes = 0.0;       // bytes this rank has stored into peer memory (the fused slab exchange)
     size_t bytes = 0;
     bool prof_on = false;
     struct ProfRec { int cls; cudaEvent_t a, b; };
@@ -264,6 +267,7 @@ struct PassSpec {
     int nzv;
     bool in_w, out_w, outer_w;
     bool p2p_out = false;    // store each destination rank's block into that rank's buffer (peer memory)
+    bool copy_only = false;  // measurement only: same tiles, no transform
 };
 static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* const* dst, int field0, int field_cnt, cudaStream_t st = nullptr) {
     if (!st) st = h->stream;
@@ -272,6 +276,7 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
     for (int f = 0; f < field_cnt; ++f) { a.src[f] = src[field0 + f]; a.dst[f] = dst[field0 + f]; }
     a.tw = h->tw;
     a.nzv = ps.nzv;
+    a.copy_only = ps.copy_only ? 1 : 0;
     const int N = h->N, K = h->kmax;
     a.in_zero_lo = ps.in_w ? K + 1 : N;  a.in_zero_hi = ps.in_w ? N - K : N;
     a.out_skip_lo = ps.out_w ? K + 1 : N; a.out_skip_hi = ps.out_w ? N - K : N;
@@ -347,7 +352,8 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
     // the persistent kernel also serves the overlapped multi-GPU schedule: a link-bound store phase runs on a
     // restricted grid (link_ctas SMs) so that the other stream's HBM-bound pass gets the rest of the GPU
     const bool link_limited = ps.p2p_out && h->overlap && h->link_ctas > 0;
-    const bool pipe = (h->use_pipe || link_limited) && h->use_tma && natural_in && h->ops->strided_pipe != nullptr;
+    const bool ring = h->use_ring && !link_limited && !ps.copy_only && h->use_tma && natural_in && h->ops->strided_ring != nullptr;
+    const bool pipe = ring || ((h->use_pipe || link_limited) && h->use_tma && natural_in && h->ops->strided_pipe != nullptr);
     if (h->use_tma && natural_in && (h->ops->strided_T == 8 || pipe)) {
         memset(&maps, 0, sizeof maps);
         const int bc = pipe ? h->ops->pipe_T : 8;
@@ -364,8 +370,10 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         // minimal traffic: every carried pencil reads its non-zero inputs and writes its kept outputs once
         const double in_cnt = ps.in_w ? 2 * K + 1 : N, out_cnt = ps.out_w ? 2 * K + 1 : N;
         const double bytes = 16.0 * field_cnt * (double)n_outer * ps.nzv * (in_cnt + out_cnt);
+        if (ps.p2p_out) h->link_bytes += 16.0 * field_cnt * (double)n_outer * ps.nzv * out_cnt * (h->nranks - 1) / h->nranks;
         ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD), bytes, st);
-        if (pipe) CKI(h->ops->strided_pipe(ps.dir, &a, mp, n_outer, field_cnt, link_limited ? h->link_ctas : h->pipe_ctas, st));
+        if (ring) CKI(h->ops->strided_ring(ps.dir, &a, mp, n_outer, field_cnt, h->sm_count, st));
+        else if (pipe) CKI(h->ops->strided_pipe(ps.dir, &a, mp, n_outer, field_cnt, link_limited ? h->link_ctas : h->pipe_ctas, st));
         else CKI(h->ops->strided(ps.dir, &a, mp, n_outer, field_cnt, st));
     }
     h->launches++;
@@ -740,6 +748,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     { const char* e = getenv("NSB200_NO_TMA"); h->use_tma = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_NO_FUSE_CURL"); h->fuse_curl = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_PIPE"); h->use_pipe = (e && e[0] == '1'); }
+    { const char* e = getenv("NSB200_RING"); h->use_ring = !(e && e[0] == '0') && !h->use_pipe; }
     h->link_ctas = (h->nranks >= 8) ? 128 : 96;   // measured: 4 ranks 11.22 -> 10.58 ms (96), 8 ranks 6.26 -> 6.02 ms (128)
     { const char* e = getenv("NSB200_LINK_CTAS"); if (e) h->link_ctas = atoi(e); }
     h->ops = ops;
@@ -877,12 +886,11 @@ int nsb200_local_slab(nsb200_ctx* h, long* local_nx, long* local_nx_start) {
 long nsb200_local_fourier_elems(nsb200_ctx* h) { return h ? 3L * h->nx_loc * h->N * h->nzf : 0; }
 long nsb200_launch_count(nsb200_ctx* h) { return h ? h->launches : 0; }
 long nsb200_device_bytes(nsb200_ctx* h) { return h ? (long)h->bytes : 0; }
+double nsb200_link_bytes(nsb200_ctx* h) { return h ? h->link_bytes : 0.0; }
 
-static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
-    h->curl_of = nullptr;   // the staging area overlaps the workspace
-    const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
-    cplx* stage = h->W[0];   // W is one contiguous 6-field buffer >= the 3-field host layout
-    CK(cudaMemcpyAsync(stage, host, n * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+// staging area (reference host layout, W[0..] is one contiguous 6-field buffer >= the 3-field host array) -> planar fields
+static int upload_staged(nsb200_ctx* h, cplx* const* dst) {
+    cplx* stage = h->W[0];
     if (h->cyclic) {
         CKR(gpu_barrier(h));   // nobody still reads the destination arrays
         k_aos_to_planar_scatter<<<h->row_grid(), 128, 0, h->stream>>>(stage, dst[0], dst[1], dst[2], h->geom_api(), h->x_start, h->nranks, peer_table(h));
@@ -896,9 +904,15 @@ static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
     h->launches++;
     return 0;
 }
-static int download_from(nsb200_ctx* h, double* host, cplx* const* src) {
-    h->curl_of = nullptr;
+static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
+    h->curl_of = nullptr;   // the staging area overlaps the workspace
     const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
+    CK(cudaMemcpyAsync(h->W[0], host, n * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    return upload_staged(h, dst);
+}
+// planar fields -> staging area in the reference host layout
+static int download_stage(nsb200_ctx* h, cplx* const* src) {
+    h->curl_of = nullptr;
     cplx* stage = h->W[0];
     if (h->cyclic) {
         CKR(gpu_barrier(h));   // every rank's source arrays are final
@@ -911,8 +925,42 @@ static int download_from(nsb200_ctx* h, double* host, cplx* const* src) {
         CK(cudaGetLastError());
         h->launches++;
     }
-    CK(cudaMemcpyAsync(host, stage, n * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+static int download_from(nsb200_ctx* h, double* host, cplx* const* src) {
+    CKR(download_stage(h, src));
+    const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
+    CK(cudaMemcpyAsync(host, h->W[0], n * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// Host <-> staging copy of the dealias cube only: the modes with |kx|, |ky| <= N/3 and kz <= N/3 of the local slab
+// (8/27 of the array) as up to four pitched 3-D copies; rows are (K+1)*3 contiguous complex numbers.
+static int copy_window(nsb200_ctx* h, cplx* stage, double* host, bool to_host) {
+    const int N = h->N, K = h->kmax;
+    const size_t el = 3 * sizeof(cplx), pitch = (size_t)h->nzf * el;
+    const int jr[2][2] = {{0, K + 1}, {N - K, N}};
+    // local planes whose global index lies in [0, K] or [N-K, N)
+    int ir[2][2] = {{0, 0}, {0, 0}};
+    ir[0][0] = 0; ir[0][1] = std::min(h->nx_loc, std::max(0, K + 1 - h->x_start));
+    ir[1][0] = std::min(h->nx_loc, std::max(0, N - K - h->x_start)); ir[1][1] = h->nx_loc;
+    if (ir[1][0] < ir[0][1]) ir[1][0] = ir[0][1];
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            const int ni = ir[a][1] - ir[a][0], nj = jr[b][1] - jr[b][0];
+            if (ni <= 0 || nj <= 0) continue;
+            cudaMemcpy3DParms p;
+            memset(&p, 0, sizeof p);
+            cudaPitchedPtr dev = make_cudaPitchedPtr(stage, pitch, pitch, (size_t)N);
+            cudaPitchedPtr hst = make_cudaPitchedPtr(host, pitch, pitch, (size_t)N);
+            p.srcPtr = to_host ? dev : hst;
+            p.dstPtr = to_host ? hst : dev;
+            p.srcPos = p.dstPos = make_cudaPos(0, (size_t)jr[b][0], (size_t)ir[a][0]);
+            p.extent = make_cudaExtent((size_t)(K + 1) * el, (size_t)nj, (size_t)ni);
+            p.kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+            CK(cudaMemcpy3DAsync(&p, h->stream));
+        }
     return 0;
 }
 
@@ -928,6 +976,28 @@ int nsb200_download_uhat(nsb200_ctx* h, double* u_hat_host) {
     if (!h || !u_hat_host) return fail("nsb200_download_uhat: null argument");
     CKR(set_device(h));
     return download_from(h, u_hat_host, h->U);
+}
+int nsb200_upload_uhat_window(nsb200_ctx* h, const double* u_hat_host) {
+    if (!h || !u_hat_host) return fail("nsb200_upload_uhat_window: null argument");
+    if (h->dealias != NSB200_DEALIAS_23) return nsb200_upload_uhat(h, u_hat_host);
+    CKR(set_device(h));
+    h->curl_of = nullptr;
+    const size_t n = (size_t)3 * h->nx_loc * h->N * h->nzf;
+    CK(cudaMemsetAsync(h->W[0], 0, n * sizeof(cplx), h->stream));
+    CKR(copy_window(h, h->W[0], const_cast<double*>(u_hat_host), false));
+    CKR(upload_staged(h, h->U));
+    CKR(check_state_support(h));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int nsb200_download_uhat_window(nsb200_ctx* h, double* u_hat_host) {
+    if (!h || !u_hat_host) return fail("nsb200_download_uhat_window: null argument");
+    if (!h->u_in_window) return nsb200_download_uhat(h, u_hat_host);
+    CKR(set_device(h));
+    CKR(download_stage(h, h->U));
+    CKR(copy_window(h, h->W[0], u_hat_host, true));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 int nsb200_rk4_step(nsb200_ctx* h, double dt) {
@@ -1223,6 +1293,13 @@ int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_
             case NSB200_OP_PASS_Z: CKR(run_z(h, NSB_Z_C2R, 3, h->W, h->nzp, h->nzf, h->nzf)); break;
             case NSB200_OP_Z_FUSED: CKR(run_z(h, NSB_Z_FUSED, 3, h->W, h->nzp, h->nzf, h->nzf)); break;
             case NSB200_OP_RK_POINTWISE: CKR(rk_stage(h, 1, dt, h->nzp, false, h->R)); break;
+            case NSB200_OP_TILE_COPY_Y:
+            case NSB200_OP_TILE_COPY_X: {
+                PassSpec ps = {op == NSB200_OP_TILE_COPY_Y ? 'y' : 'x', INV, 'n', h->nzp, h->nzp, h->nzf, false, false, false};
+                ps.copy_only = true;
+                CKR(run_pass(h, ps, h->W, h->W + 3, 0, 3));
+                break;
+            }
             case NSB200_OP_L2_FLUSH: CK(cudaMemsetAsync(h->flush_buf, it & 0xff, h->flush_bytes, h->stream)); break;
             default: return fail("nsb200_time_op: unknown op");
         }

@@ -259,9 +259,15 @@ __global__ void k_rk_stage(const RkArgs a) {
             const long long e = base + k;
             // outside the window the forward transform was not stored: the dealias mask makes it zero
             const bool in = row_in && k <= g.kcut;
-            cplx c[3];
+            // every input of the mode is requested before the first use: the stores below may alias the loads as far as
+            // the compiler knows, so loads left between them would be serialised into four dependent round trips to HBM
+            cplx c[3], u0[3], ac[3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) c[d] = in ? a.c[d][cbase + k] : mk(0.0, 0.0);
+            for (int d = 0; d < 3; ++d) c[d] = in ? NSB_LDCG(a.c[d] + cbase + k) : mk(0.0, 0.0);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) u0[d] = (a.stage != 4) ? NSB_LDCG(a.u[d] + e) : mk(0.0, 0.0);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) ac[d] = (a.stage >= 1 && a.stage <= 3) ? NSB_LDCG(a.acc[d] + e) : mk(0.0, 0.0);
             project_mode(kx, ky, k, a.norm, a.dealias, a.kmax2, c[0], c[1], c[2]);
             if (a.stage == 4) {
 #pragma unroll
@@ -275,8 +281,8 @@ __global__ void k_rk_stage(const RkArgs a) {
                 for (int d = 0; d < 3; ++d) {
                     cplx bk = rmul(bcoef, c[d]);
                     if (a.euler) bk = rmul(a.dt, bk);
-                    a.acc[d][e] = (a.stage == 0) ? bk : caddr(a.acc[d][e], bk);
-                    c[d] = caddr(a.u[d][e], rmul(acoef, c[d]));   // next stage input
+                    a.acc[d][e] = (a.stage == 0) ? bk : caddr(ac[d], bk);
+                    c[d] = caddr(u0[d], rmul(acoef, c[d]));   // next stage input
                     a.tmp[d][e] = c[d];
                 }
             } else {
@@ -295,9 +301,8 @@ __global__ void k_rk_stage(const RkArgs a) {
                 for (int d = 0; d < 3; ++d) {
                     cplx bk = rmul(bcoef, c[d]);
                     if (a.euler) bk = rmul(a.dt, bk);
-                    const cplx comb = caddr(a.acc[d][e], bk);
-                    const cplx u = a.u[d][e];
-                    c[d] = a.euler ? caddr(u, comb) : caddr(rmul(f1, u), rmul(f2, comb));   // new state = next step's input
+                    const cplx comb = caddr(ac[d], bk);
+                    c[d] = a.euler ? caddr(u0[d], comb) : caddr(rmul(f1, u0[d]), rmul(f2, comb));   // new state = next step's input
                     a.uout[d][e] = c[d];
                 }
             }

@@ -94,11 +94,16 @@ class Solver:
         self.lib.check(self.lib.nsb200_download_real(self.h, 0 if which == "u" else 1, out.ctypes.data), "nsb200_download_real")
         return out
 
-    def upload_ptr(self, ptr):
-        self.lib.check(self.lib.nsb200_upload_uhat(self.h, ptr), "nsb200_upload_uhat")
+    def upload_ptr(self, ptr, window=False):
+        fn = self.lib.nsb200_upload_uhat_window if window else self.lib.nsb200_upload_uhat
+        self.lib.check(fn(self.h, ptr), "nsb200_upload_uhat")
 
-    def download_ptr(self, ptr):
-        self.lib.check(self.lib.nsb200_download_uhat(self.h, ptr), "nsb200_download_uhat")
+    def download_ptr(self, ptr, window=False):
+        fn = self.lib.nsb200_download_uhat_window if window else self.lib.nsb200_download_uhat
+        self.lib.check(fn(self.h, ptr), "nsb200_download_uhat")
+
+    def link_bytes(self):
+        return float(self.lib.nsb200_link_bytes(self.h))
 
     def initial_conditions(self, name, seed=123456789, kp=4.0, energy=math.pi ** 3):
         """InitialConditions (solver.c:1537): TAYLOR_GREEN, SHAPIRO or the synthetic RANDOM_PHASE."""

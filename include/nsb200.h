@@ -83,6 +83,15 @@ long nsb200_local_fourier_elems(nsb200_ctx* h);
 /* run_data->u_hat  <->  device state (the state lives on the GPU between steps). */
 int nsb200_upload_uhat(nsb200_ctx* h, const double* u_hat_host);
 int nsb200_download_uhat(nsb200_ctx* h, double* u_hat_host);
+/* The same for arrays that are known to be dealiased, as every state the reference's loop produces is
+ * (ApplyDealiasing, solver.c:727,1630): only the modes inside the cube |kx|, |ky| <= Nx/3, kz <= Nx/3 (8/27 of the
+ * array, which contains the 2/3 sphere) cross PCIe.
+ *   upload:   the caller guarantees u_hat_host vanishes outside the cube (what lies there is not read);
+ *   download: writes the cube only; the caller guarantees the rest of u_hat_host already holds zeros (true for an
+ *             array that nsb200_download_uhat has filled once, or that ApplyDealiasing has been applied to).
+ * Both fall back to the full transfer when dealiasing is off or the resident state is not confined to the cube. */
+int nsb200_upload_uhat_window(nsb200_ctx* h, const double* u_hat_host);
+int nsb200_download_uhat_window(nsb200_ctx* h, double* u_hat_host);
 
 /* Replaces RK4Step(dt, N, local_Nx, RK_data) (solver.c:505-608): one RK4 step of the resident
  * state, four NonlinearRHSBatch evaluations, viscous (or Euler) final update. */
@@ -153,6 +162,8 @@ int nsb200_host_unregister(void* ptr);
 #define NSB200_OP_L2_FLUSH 5
 #define NSB200_OP_Z_FUSED 6
 #define NSB200_OP_RK_POINTWISE 7
+#define NSB200_OP_TILE_COPY_Y 8 /* the strided passes' tile traffic (TMA tile in, 128-byte segments out) without the transform: */
+#define NSB200_OP_TILE_COPY_X 9 /* the ceiling the access pattern itself allows, 3 fields                                      */
 int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_ms);
 /* Per-kernel-class timing: while enabled every kernel launch of the handle is bracketed by CUDA events
  * on the launching stream; nsb200_profile_read synchronises, returns the summed device time (ms) and
@@ -176,6 +187,9 @@ int nsb200_profile_bytes(nsb200_ctx* h, double bytes[NSB200_PC_COUNT]);
 long nsb200_launch_count(nsb200_ctx* h);
 /* Bytes of device memory held by the handle. */
 long nsb200_device_bytes(nsb200_ctx* h);
+/* Bytes this rank has stored into peer GPUs' memory since creation (the slab exchange fused into the FFT store
+ * phases, NVLink); 0 on one rank or with the NCCL fallback exchange. */
+double nsb200_link_bytes(nsb200_ctx* h);
 
 #ifdef __cplusplus
 }

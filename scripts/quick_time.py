@@ -25,6 +25,8 @@ for n in sizes:
         rows = [
             ("pass_y (3 fields)", capi.OP_PASS_Y, 6 * S, 20),
             ("pass_x (3 fields)", capi.OP_PASS_X, 6 * S, 20),
+            ("tile copy y (3 f)", capi.OP_TILE_COPY_Y, 6 * S, 20),
+            ("tile copy x (3 f)", capi.OP_TILE_COPY_X, 6 * S, 20),
             ("z_c2r  (3 fields)", capi.OP_PASS_Z, 6 * S, 20),
             ("z_fused (6 -> 3)", capi.OP_Z_FUSED, 9 * S, 20),
             ("rk pointwise", capi.OP_RK_POINTWISE, 15 * S, 20),

@@ -30,6 +30,9 @@ def test_reference_arm_line():
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # every timed sample is a full RK4Step: the line reports what was actually timed, nothing is extrapolated
+    assert d["extrapolated"] is False and d["steps"] >= 1 and "full RK4Step at 64^3" in cb["sample"]
+    assert d["steps_requested"] == 1
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
@@ -39,8 +42,11 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
     assert p.returncode == 0 and p.stdout.strip() == ""
 
 
-def test_committed_gpu_bench_record_has_the_contract_keys():
-    path = os.path.join(ROOT, "profiles", "r01_bench_final_1gpu.json")
+@pytest.mark.parametrize("name", ["r01_bench_final_1gpu.json", "r02_bench_1gpu.json"])
+def test_committed_gpu_bench_record_has_the_contract_keys(name):
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        pytest.skip("%s not recorded yet" % name)
     d = json.loads([l for l in open(path) if l.startswith("{")][-1])
     assert BASE_KEYS <= set(d)
     assert d["n_gpus"] == 1 and d["config"]["N"] == 512 and d["dtype"] == "f64" and d["data"] == "synthetic"
@@ -56,3 +62,6 @@ def test_committed_gpu_bench_record_has_the_contract_keys():
     assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] > 0
+    if name.startswith("r02"):
+        assert d["parity"]["ok"] is True and d["parity"]["max_rel_err"] < 1e-12
+        assert "save_interval_%d" % d["steps"] in e and "step_frac_204S" not in r

@@ -55,6 +55,31 @@ def test_apply_dealiasing_bit_exact(n, dim):
         assert np.array_equal(s.apply_dealiasing(a), o.apply_dealiasing(a, s.N))
 
 
+@pytest.mark.parametrize("n", [32, 128])
+def test_windowed_transfers_move_the_dealias_cube_only(n):
+    """nsb200_upload_uhat_window / _download_uhat_window: same state as the full transfers for dealiased arrays."""
+    with nsb.Solver(n, nu=0.01) as s:
+        s.initial_conditions("RANDOM_PHASE", seed=5, kp=4.0)
+        full = s.get_u_hat()
+        win = np.zeros_like(full)
+        s.download_ptr(win.ctypes.data, window=True)
+        assert np.array_equal(win, full)
+        # outside the cube nothing is written (the caller's zeros stay) and nothing is read
+        K = n // 3
+        marked = np.full_like(full, 7.0)
+        s.download_ptr(marked.ctypes.data, window=True)
+        inside = np.zeros(full.shape[:3], dtype=bool)
+        ii = np.r_[0:K + 1, n - K:n]
+        inside[np.ix_(ii, ii, np.arange(K + 1))] = True
+        assert np.array_equal(marked[inside], full[inside]) and np.all(marked[~inside] == 7.0)
+        s.rk4_step(1e-3)
+        ref = s.get_u_hat()
+        marked[inside] = full[inside]
+        s.upload_ptr(marked.ctypes.data, window=True)          # the 7s outside the cube must not be read
+        s.rk4_step(1e-3)
+        assert np.array_equal(s.get_u_hat(), ref)
+
+
 def test_errors_are_reported_not_swallowed():
     with pytest.raises(RuntimeError, match="power of two"):
         nsb.Solver(48)
