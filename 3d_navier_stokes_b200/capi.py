@@ -13,6 +13,7 @@ _LP = ctypes.POINTER(ctypes.c_long)
 SYMBOLS = [
     ("nsb200_version", ctypes.c_char_p, []),
     ("nsb200_last_error", ctypes.c_char_p, []),
+    ("nsb200_device_count", ctypes.c_int, []),
     ("nsb200_create", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), _LP, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     ("nsb200_destroy", ctypes.c_int, [ctypes.c_void_p]),

@@ -106,11 +106,13 @@ int strided_ring(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer
     if (pa.total_tiles == 0) return 0;
     // Short runs of consecutive tiles per CTA, many CTAs: the CTAs resident at any time then sweep one compact region of
     // the field (neighbouring kz tiles of the same rows), which keeps the DRAM pages they share open; one long run per
-    // SM (343 tiles) measured 1.39 ms per 3-field pass against 1.14 ms with runs of 6-12.
-    static int tpc = 0;
-    if (tpc == 0) { const char* e = getenv("NSB200_RING_TPC"); tpc = e ? atoi(e) : 12; if (tpc < 1) tpc = 12; }
-    (void)max_ctas;
-    pa.tiles_per_cta = tpc;
+    // SM (343 tiles) measured 1.39 ms per 3-field pass against 1.14 ms with runs of 6-12.  The run length is chosen so
+    // that the CTAs fill whole waves of the max_ctas SMs as evenly as possible (small multi-GPU launches).
+    static int tpc_max = 0;
+    if (tpc_max == 0) { const char* e = getenv("NSB200_RING_TPC"); tpc_max = e ? atoi(e) : 12; if (tpc_max < 1) tpc_max = 12; }
+    const int per_wave = max_ctas > 0 ? max_ctas : 148;
+    const int waves = (pa.total_tiles + per_wave * tpc_max - 1) / (per_wave * tpc_max);
+    pa.tiles_per_cta = (pa.total_tiles + per_wave * waves - 1) / (per_wave * waves);
     const int grid = (pa.total_tiles + pa.tiles_per_cta - 1) / pa.tiles_per_cta;
     if (dir == FWD) k_fft_strided_ring<BP, FWD><<<grid, RingCfg<BP>::THREADS, RingCfg<BP>::SMEM, s>>>(*a, *maps, pa);
     else k_fft_strided_ring<BP, INV><<<grid, RingCfg<BP>::THREADS, RingCfg<BP>::SMEM, s>>>(*a, *maps, pa);

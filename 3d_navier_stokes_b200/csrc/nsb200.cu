@@ -298,9 +298,15 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
             if (ps.exch == 'o') {
                 exchange_layout(N, h->nranks, ps.out_rs, L);
                 a.out_shift = (int)L[0]; a.out_mask = (int)L[1]; a.out_s1 = L[2]; a.out_so = L[3];
-                if (ps.p2p_out) {   // receiver-side layout [source rank][kx_loc][y_loc][rs]: this rank's block
+                if (ps.p2p_out) {
+                    // Peer stores: plane li of this rank goes to row kx of the receiver's [kx][y_loc][rs] buffer, in
+                    // NATURAL kx order (kx = li*P + rank with the cyclic distribution, rank*nx_loc + li with contiguous
+                    // slabs), so the receiving x pass reads an ordinary field (TMA tiles, persistent ring pass).
                     a.out_p2p = 1; a.out_s1 = 0;
-                    for (int f = 0; f < field_cnt; ++f) a.dst[f] += (long long)h->rank * L[2];
+                    const long long row = (long long)h->ny_loc * ps.out_rs;          // one kx row of the receiver
+                    a.out_so = h->cyclic ? row * h->nranks : row;
+                    const long long first = h->cyclic ? row * h->rank : row * h->rank * h->nx_loc;
+                    for (int f = 0; f < field_cnt; ++f) a.dst[f] += first;
                     for (int r = 0; r < h->nranks; ++r) a.peer_delta[r] = h->peer_delta[r];
                 }
             } else {
@@ -312,35 +318,19 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         n_outer = h->ny_loc;
         a.in_so = ps.in_rs;  a.in_s2 = (long long)h->ny_loc * ps.in_rs;
         a.out_so = ps.out_rs; a.out_s2 = (long long)h->ny_loc * ps.out_rs;
-        if (h->cyclic) {
-            // the received blocks are [source rank r][local plane li][y_loc][rs] and hold kx = li*P + r
-            long L[5];
+        if (ps.p2p_out) {
+            // forward x pass, peer stores: output plane kx belongs to rank kx % P (cyclic; local index kx / P) or
+            // kx / nx_loc (contiguous slabs; local index kx % nx_loc); it lands in the owner's NATURAL Fourier slab
+            // [kx_loc][y][rs] at y = rank * ny_loc + y_local, the ordinary input of the forward y pass
             int lp = 0;
             while ((1 << lp) < h->nranks) ++lp;
-            if (ps.dir == INV) {      // kx is the INPUT axis: n -> (n & (P-1)) * block + (n >> lp) * plane
-                exchange_layout(N, h->nranks, ps.in_rs, L);
-                a.in_shift = lp; a.in_mask = h->nranks - 1; a.in_s1 = (long long)h->ny_loc * ps.in_rs; a.in_s2 = L[2];
-            } else if (!ps.p2p_out) { // forward, NCCL exchange: same layout on the OUTPUT side
-                exchange_layout(N, h->nranks, ps.out_rs, L);
-                a.out_shift = lp; a.out_mask = h->nranks - 1; a.out_s1 = (long long)h->ny_loc * ps.out_rs; a.out_s2 = L[2];
-            }
-        }
-        if (ps.p2p_out && h->cyclic) {
-            long L[5];
-            int lp = 0;
-            while ((1 << lp) < h->nranks) ++lp;
-            exchange_layout(N, h->nranks, ps.out_rs, L);
-            a.out_p2p = 1; a.out_rank_lo = 1; a.out_shift = lp; a.out_mask = h->nranks - 1; a.out_s1 = 0;
-            a.out_s2 = (long long)h->ny_loc * ps.out_rs;   // local plane stride in the receiver's block
-            for (int f = 0; f < field_cnt; ++f) a.dst[f] += (long long)h->rank * L[2];
-            for (int r = 0; r < h->nranks; ++r) a.peer_delta[r] = h->peer_delta[r];
-        } else if (ps.p2p_out) {
-            // forward x pass: output plane kx belongs to rank kx / nx_loc; it lands in that rank's buffer at
-            // [this rank (y-slab owner)][kx_loc][y_loc][rs], the input layout of the forward y pass
             long L[5];
             exchange_layout(N, h->nranks, ps.out_rs, L);
-            a.out_p2p = 1; a.out_shift = (int)L[0]; a.out_mask = (int)L[1]; a.out_s1 = 0;
-            for (int f = 0; f < field_cnt; ++f) a.dst[f] += (long long)h->rank * L[2];
+            a.out_p2p = 1; a.out_s1 = 0;
+            if (h->cyclic) { a.out_rank_lo = 1; a.out_shift = lp; a.out_mask = h->nranks - 1; }
+            else { a.out_shift = (int)L[0]; a.out_mask = (int)L[1]; }
+            a.out_s2 = (long long)N * ps.out_rs;                               // plane stride of the receiver's slab
+            for (int f = 0; f < field_cnt; ++f) a.dst[f] += (long long)h->rank * h->ny_loc * ps.out_rs;
             for (int r = 0; r < h->nranks; ++r) a.peer_delta[r] = h->peer_delta[r];
         }
     }
@@ -466,22 +456,25 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx***
     for (int d = 0; d < 3; ++d) { ca.u[d] = in[d]; ca.w[d] = h->p2p ? h->W[d] : h->R[3 + d]; }
     ca.g = h->geom(in_w);
     ca.w_rs = rs;
-    const bool have_curl = h->fuse_curl && h->curl_of == in[0] && h->curl_rs == rs && h->curl_win == in_w && !(h->p2p && h->overlap);
+    const bool have_curl = h->fuse_curl && h->curl_of == in[0] && h->curl_rs == rs && h->curl_win == in_w;
     h->curl_of = nullptr;   // consumed (the buffer is overwritten further down the pipeline)
+    const bool two_streams = h->p2p && h->overlap;
+    if (two_streams) {
+        // the second stream starts from the state the first one has reached: `in`, the workspace and (when the RK
+        // kernel has already written it) w = i k x in are ready
+        CK(cudaEventRecord(h->ev_c, h->stream));
+        CK(cudaStreamWaitEvent(h->comm_stream, h->ev_c, 0));
+    }
     if (!have_curl) {
         // with the overlapped multi-GPU schedule the curl runs on the second stream, beside the y pass of u
-        cudaStream_t cs = (h->p2p && h->overlap) ? h->comm_stream : h->stream;
-        if (cs != h->stream) {
-            CK(cudaEventRecord(h->ev_c, h->stream));       // `in` and the workspace are ready
-            CK(cudaStreamWaitEvent(cs, h->ev_c, 0));
-        }
+        cudaStream_t cs = two_streams ? h->comm_stream : h->stream;
         const double kw = in_w ? 2.0 * h->kmax + 1 : h->N;   // kx planes are counted globally / nranks (slab average)
         ProfScope ps(h, NSB200_PC_CURL, 16.0 * 6.0 * (kw * kw / h->nranks) * nz_in, cs);
         k_curl<<<rg, nsb200_ctx::row_block(nz_in), 0, cs>>>(ca);
-        if (cs != h->stream) CK(cudaEventRecord(h->ev_fork, cs));
         CK(cudaGetLastError());
         h->launches++;
     }
+    if (two_streams) CK(cudaEventRecord(h->ev_fork, h->comm_stream));   // w is ready on the second stream
     cplx* src[6] = {in[0], in[1], in[2], h->R[3], h->R[4], h->R[5]};
     const bool multi = h->nranks > 1;
     //                axis dir  exch            in_rs    out_rs nzv     in_w   out_w  outer_w
@@ -506,6 +499,7 @@ static int rhs_raw(nsb200_ctx* h, cplx* const* in, bool in_w, int* c_rs, cplx***
         cplx* srcp[6] = {in[0], in[1], in[2], h->W[0], h->W[1], h->W[2]};
         yinv_u.p2p_out = yinv_w.p2p_out = true;
         xfwd.p2p_out = true;
+        yfwd.exch = 'n';             // the peers store straight into the natural [kx_loc][y][kz] slab
         if (h->overlap) {
             // Two streams: while one field group drains over NVLink (store phase of the y / forward-x pass), the
             // other group's HBM-bound local pass runs.  The curl was launched on S1 above (ev_fork).
@@ -669,7 +663,11 @@ static int fft3_c2r_inplace(nsb200_ctx* h) {
 // ------------------------------------------------------------------------------ C ABI
 extern "C" {
 
-const char* nsb200_version(void) { return "nsb200 0.1 sm_100a"; }
+const char* nsb200_version(void) { return "nsb200 0.2 sm_100a"; }
+int nsb200_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 const char* nsb200_last_error(void) { return g_err.c_str(); }
 
 int nsb200_exchange_layout(long N, int n_ranks, long row_stride, long out[5]) {

@@ -6,8 +6,9 @@
  *   NonlinearRHSBatch         solver.c:620   -> nsb200_nonlinear_rhs (host arrays in, host arrays out)
  *   ComputeSystemMeasurables  solver.c:1142  -> nsb200_measure + nsb200_assemble_measurables
  *   ApplyDealiasing           solver.c:1709  -> nsb200_apply_dealiasing
- *   WriteDataToFile / FinalWriteAndCloseOutputFile (hdf5_funcs.c:492,1028) are wrapped only to copy the
- *   device state back into run_data->u_hat before the reference's own writer runs.
+ *   CreateOutputFilesWriteICs / WriteDataToFile / FinalWriteAndCloseOutputFile (hdf5_funcs.c:33,492,1028) are wrapped
+ *   only to copy the device state back into run_data->u_hat (and to fill run_data->w_hat, which the reference writes
+ *   but never computes - SURVEY Q13) before the reference's own writer runs.
  *
  * This file is compiled against the reference's data_types.h / solver.h where they lie (it is the
  * reference-side half of the binding); host/Makefile links it with the reference's unmodified main.c,
@@ -24,12 +25,14 @@
 #include "solver.h"
 #include "nsb200.h"
 
+void ref_CreateOutputFilesWriteICs(const long int* N, double dt);
 void ref_WriteDataToFile(double t, double dt, long int iters);
 void ref_FinalWriteAndCloseOutputFile(const long int* N, int iters, int save_data_indx);
 
 static nsb200_ctx* g_h = NULL;
 static int g_host_newer = 1;   /* run_data->u_hat holds data the device has not seen (initial condition) */
 static int g_dev_newer = 0;    /* the device state is ahead of run_data->u_hat */
+static int g_host_full = 0;    /* run_data->u_hat has been filled completely by a download: later ones move the dealias cube only */
 
 static void die(const char* what) {
 	fprintf(stderr, "\n["RED"ERROR"RESET"] --- %s: %s\n-->> Exiting!!!\n", what, nsb200_last_error());
@@ -53,11 +56,18 @@ static void ensure(void) {
 	memset(uid, 0, sizeof uid);
 	if (sys_vars->num_procs > 1) {
 		if (!sys_vars->rank && nsb200_get_nccl_unique_id(uid)) die("nsb200_get_nccl_unique_id");
-		/* MPI_BYTE is not in the single-rank stand-in; a real MPI build broadcasts the 128 bytes: */
-		MPI_Allreduce(MPI_IN_PLACE, uid, 32, MPI_INT, MPI_SUM, MPI_COMM_WORLD);   /* zeros elsewhere: sum == bcast */
+#if defined(MPI_BYTE)
+		MPI_Bcast(uid, 128, MPI_BYTE, 0, MPI_COMM_WORLD);
+#else   /* the single-rank stand-in has no MPI_Bcast / MPI_BYTE; the other ranks hold zeros, so a sum is a broadcast */
+		MPI_Allreduce(MPI_IN_PLACE, uid, 32, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+#endif
 	}
+	/* one rank per GPU of the node: global rank modulo the visible devices (ranks are placed node by node by mpirun;
+	 * NSB200_DEVICE overrides, e.g. with a node-local rank from the launcher) */
 	const char* dev_env = getenv("NSB200_DEVICE");
-	const int device = dev_env ? atoi(dev_env) : sys_vars->rank;
+	int ndev = nsb200_device_count();
+	if (ndev < 1) die("nsb200_device_count");
+	const int device = dev_env ? atoi(dev_env) : sys_vars->rank % ndev;
 	if (nsb200_create(&g_h, sys_vars->N, device, sys_vars->NU, visc_pow, system, NSB200_DEALIAS_23,
 	                  sys_vars->rank, sys_vars->num_procs, sys_vars->num_procs > 1 ? uid : NULL)) die("nsb200_create");
 	long lnx = 0, lstart = 0;
@@ -67,6 +77,8 @@ static void ensure(void) {
 		        lstart, lnx, sys_vars->local_Nx_start, sys_vars->local_Nx);
 		exit(1);
 	}
+	/* pin run_data->u_hat so that the state transfers run at the full PCIe rate (failure is not fatal: pageable copies) */
+	nsb200_host_register(run_data->u_hat, (unsigned long long)sizeof(fftw_complex) * 3 * sys_vars->local_Nx * sys_vars->N[1] * (sys_vars->N[2] / 2 + 1));
 	atexit(hooks_atexit);
 }
 /* Restart / external initial condition.  The reference parses `-z <file>` (utils.c:209-215)
@@ -105,9 +117,21 @@ static void to_device(void) {
 }
 static void to_host(void) {
 	if (g_h && g_dev_newer) {
-		if (nsb200_download_uhat(g_h, (double*)run_data->u_hat)) die("nsb200_download_uhat");
+		/* after one full download the array holds exact zeros outside the dealias cube and only this file writes it */
+		if (g_host_full ? nsb200_download_uhat_window(g_h, (double*)run_data->u_hat) : nsb200_download_uhat(g_h, (double*)run_data->u_hat))
+			die("nsb200_download_uhat");
+		g_host_full = 1;
 		g_dev_newer = 0;
 	}
+}
+/* run_data->w_hat = i k x u_hat of the resident state: a dataset of the reference's file (hdf5_funcs.c:186,639) that its
+ * own code leaves zero */
+static void fill_w_hat(void) {
+#if defined(__VORT_FOUR)
+	ensure();
+	to_device();
+	if (nsb200_download_what(g_h, (double*)run_data->w_hat)) die("nsb200_download_what");
+#endif
 }
 
 void RK4Step(const double dt, const long int* N, const ptrdiff_t local_Nx, RK_data_struct* RK_data) {
@@ -129,7 +153,7 @@ void ApplyDealiasing(fftw_complex* array, int array_dim, const long int* N) {
 	ensure();
 	if (array == run_data->u_hat) to_host();
 	if (nsb200_apply_dealiasing(g_h, (double*)array, array_dim)) die("nsb200_apply_dealiasing");
-	if (array == run_data->u_hat) g_host_newer = 1;
+	if (array == run_data->u_hat) { g_host_newer = 1; g_host_full = 0; }
 }
 
 void ComputeSystemMeasurables(int iter) {
@@ -161,15 +185,27 @@ void ComputeSystemMeasurables(int iter) {
 		ws = run_data->enst_spect;
 #endif
 		if (nsb200_spectra(g_h, es, ws, sys_vars->n_spect)) die("nsb200_spectra");
+		/* nsb200_spectra returns GLOBAL sums on every rank and the reference MPI_Reduce(SUM)s these arrays before it
+		 * writes them (hdf5_funcs.c:272-276, 725-729): rank 0 carries them, the others carry zero (as for the series) */
+		if (sys_vars->rank) {
+			if (es) memset(es, 0, sizeof(double) * sys_vars->n_spect);
+			if (ws) memset(ws, 0, sizeof(double) * sys_vars->n_spect);
+		}
 	}
 #endif
 }
 
+void CreateOutputFilesWriteICs(const long int* N, double dt) {
+	fill_w_hat();
+	ref_CreateOutputFilesWriteICs(N, dt);
+}
 void WriteDataToFile(double t, double dt, long int iters) {
 	to_host();
+	fill_w_hat();
 	ref_WriteDataToFile(t, dt, iters);
 }
 void FinalWriteAndCloseOutputFile(const long int* N, int iters, int save_data_indx) {
 	to_host();
 	ref_FinalWriteAndCloseOutputFile(N, iters, save_data_indx);
+	if (g_h) nsb200_host_unregister(run_data->u_hat);   /* SpectralSolve frees it next (solver.c:207) */
 }

@@ -40,6 +40,8 @@ typedef struct nsb200_ctx nsb200_ctx;
 const char* nsb200_version(void);
 /* Message of the last failing call on this thread. */
 const char* nsb200_last_error(void);
+/* CUDA devices visible to this process (0 when there is none): the forwarding stubs bind rank r to device r % count. */
+int nsb200_device_count(void);
 
 /* Replaces AllocateMemory (solver.c:1832-2028) + InitializeFFTWPlans (solver.c:2034-2073) +
  * InitializeSpaceVariables (solver.c:1764-1826) for the device side.

@@ -68,6 +68,19 @@ void ref_measure(double out[5]) {
 	out[0] = run_data->tot_energy[0]; out[1] = run_data->tot_enstr[0]; out[2] = run_data->tot_palin[0];
 	out[3] = run_data->tot_heli[0]; out[4] = run_data->enrg_diss[0];
 }
+/* shell spectra as ComputeSystemMeasurables bins them (solver.c:1240-1259); returns n_spect (solver.c:1384) */
+int ref_spectra(double* enrg, double* enst) {
+	bind();
+	ComputeSystemMeasurables(0);
+#if defined(__ENRG_SPECT) && defined(__ENST_SPECT)
+	memcpy(enrg, run_data->enrg_spect, sizeof(double) * sys_vars->n_spect);
+	memcpy(enst, run_data->enst_spect, sizeof(double) * sys_vars->n_spect);
+	return sys_vars->n_spect;
+#else
+	(void)enrg; (void)enst;
+	return 0;
+#endif
+}
 void ref_apply_dealias(double* arr, int dim) { bind(); ApplyDealiasing((fftw_complex*)arr, dim, sys_vars->N); }
 void ref_wavenumbers(int* kx, int* ky, int* kz) {
 	bind();

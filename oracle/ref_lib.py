@@ -99,6 +99,14 @@ class RefSolver:
         self.lib.ref_measure(_dp(out))
         return out
 
+    def spectra(self):
+        """(EnergySpectrum, EnstrophySpectrum) of the current state, binned by the reference (solver.c:1240-1259)."""
+        e = np.zeros(4096)
+        w = np.zeros(4096)
+        self.lib.ref_spectra.argtypes = [_DP, _DP]
+        n = self.lib.ref_spectra(_dp(e), _dp(w))
+        return e[:n].copy(), w[:n].copy()
+
     def apply_dealias(self, arr):
         arr = np.ascontiguousarray(arr, dtype=np.complex128).copy()
         self.lib.ref_apply_dealias(_dp(arr), arr.shape[-1])

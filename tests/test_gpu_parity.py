@@ -261,6 +261,23 @@ def test_spectra_vs_oracle():
     assert e.sum() == pytest.approx(o.measurables(u, N, 0.0)["energy"], rel=1e-12)
 
 
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libns_ref.so not present")
+@pytest.mark.parametrize("n", [32, 64])
+def test_spectra_vs_reference_build(n):
+    """SURVEY 8f row f3 against the reference's own binning (oracle/_ref built with -D__ENRG_SPECT -D__ENST_SPECT)."""
+    N = (n, n, n)
+    u = o.random_phase_ic(N, seed=13, kp=5.0)
+    with R.RefSolver(n, nu=0.01, dt=1e-3, ic="TAYLOR_GREEN") as r, nsb.Solver(n, nu=0.01) as s:
+        r.set_uhat(u); s.set_u_hat(u)
+        for _ in range(2):
+            r.rk4_step(1e-3); s.rk4_step(1e-3)
+        e_ref, w_ref = r.spectra()
+        e, w = s.spectra()
+    assert len(e) == len(e_ref)
+    assert np.allclose(e, e_ref, rtol=1e-10, atol=1e-12 * e_ref.max())
+    assert np.allclose(w, w_ref, rtol=1e-10, atol=1e-12 * w_ref.max())
+
+
 def test_vorticity_and_real_space_dumps():
     """w_hat (Q13) and the normalised real-space fields of the save path (hdf5_funcs.c:588-602)."""
     n = 32; N = (n, n, n)

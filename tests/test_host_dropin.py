@@ -1,14 +1,18 @@
 """The reference's own program (main.c -> GetCMLArgs -> SpectralSolve, unmodified apart from fixes F1-F3/F5) with
 its hot path replaced through host/nsb200_hooks.c: same command line, same time loop, same series.
 host/_build/solver_cpu is the all-CPU control, host/_build/solver_b200 runs RK4Step / ComputeSystemMeasurables /
-NonlinearRHSBatch / ApplyDealiasing on the GPU through the C ABI.  Both are compared with the golden vectors
-that tests/golden/make_golden.py produced from the reference build (same argv)."""
+NonlinearRHSBatch / ApplyDealiasing on the GPU through the C ABI.  Both write the reference's own HDF5 files (its
+hdf5_funcs.c on host/standins/h5lite.c); the tests read them back with tests/h5parse.py and compare with the golden
+vectors that tests/golden/make_golden.py produced from the reference build (same argv)."""
 import os
 import subprocess
 import tempfile
 
 import numpy as np
 import pytest
+
+import h5parse
+from test_hdf5_output import check_reference_layout, solver_files
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "tests", "golden")
@@ -17,24 +21,19 @@ CPU = os.path.join(ROOT, "host", "_build", "solver_cpu")
 
 
 def run_solver(exe, env_extra=None):
-    g = np.load(os.path.join(G, "ref_main_tg32.npz"))
-    n = int(g["n"])
-    args = ["-n", n, "-n", n, "-n", n, "-s", 0.0, "-e", float(g["T"]), "-h", float(g["dt"]), "-v", float(g["nu"]),
-            "-i", "TAYLOR_GREEN", "-p", int(g["save_every"])]
+    """Runs the golden case; returns (golden, series rows (t, E, Enst, Palin, Heli, Diss), final u_hat, saves, stdout-free)."""
     with tempfile.TemporaryDirectory() as d:
-        env = dict(os.environ, NSB_IO_STUB_DIR=d)
-        env.update(env_extra or {})
-        p = subprocess.run([exe] + [str(a) for a in args], env=env, capture_output=True, text=True, timeout=600)
-        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
-        series = np.loadtxt(os.path.join(d, "series.txt"))
-        u = np.fromfile(os.path.join(d, "u_hat_final.bin")).view(np.complex128).reshape(n, n, n // 2 + 1, 3)
-        nw = int(open(os.path.join(d, "n_writes.txt")).read())
-    return g, series, u, nw, p.stdout
+        g, main, spec = solver_files(exe, d, env_extra)
+        series = np.stack([main.read("/" + k) for k in ("Time", "TotalEnergy", "TotalEnstrophy", "TotalPalinstrophy", "TotalHelicity",
+                                                        "EnergyDissipation")], axis=1)
+        groups = sorted(k for k in main.root.children if k.startswith("Iter_"))
+        u = main.read("/" + groups[-1] + "/u_hat")
+        return g, series, u["r"] + 1j * u["i"], len(groups) - 1, main, spec
 
 
 @pytest.mark.skipif(not os.path.exists(CPU), reason="host/_build/solver_cpu not built (make -C host)")
 def test_cpu_control_binary_matches_golden():
-    g, series, u, nw, _ = run_solver(CPU)
+    g, series, u, nw, _, _ = run_solver(CPU)
     assert nw == int(g["n_writes"])
     assert np.allclose(series[:, [0, 1, 2, 3, 5]], g["series"][:, [0, 1, 2, 3, 5]], rtol=1e-12, atol=0)
     assert np.abs(u - g["u_final"]).max() <= 1e-13 * np.abs(g["u_final"]).max()
@@ -43,20 +42,31 @@ def test_cpu_control_binary_matches_golden():
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(B200), reason="host/_build/solver_b200 not built (make -C host)")
 def test_reference_program_on_gpu_matches_golden():
-    g, series, u, nw, out = run_solver(B200)
+    g, series, u, nw, main, spec = run_solver(B200)
     assert nw == int(g["n_writes"])
     ref = g["series"]
     assert series.shape == ref.shape
     # literal diagnostics (the reference's own numbers) within the series tolerance of north_star
     assert np.allclose(series[:, [0, 1, 2, 3, 5]], ref[:, [0, 1, 2, 3, 5]], rtol=1e-10, atol=0)
     assert np.abs(u - g["u_final"]).max() <= 1e-12 * np.abs(g["u_final"]).max()
-    assert "Total Execution Time" in out
+    # the files carry the reference's whole layout ...
+    check_reference_layout(g, main, spec, 1e-12, 1e-10)
+    # ... including w_hat = i k x u_hat, which the GPU hooks fill (the reference leaves it zero)
+    import ns_oracle as o
+    n = int(g["n"])
+    w = main.read("/Iter_00010/w_hat")
+    assert np.abs((w["r"] + 1j * w["i"]) - o.curl_hat(u, (n, n, n))).max() <= 1e-12 * np.abs(u).max() * n
+    # ... and the shell spectra of the saved state (ComputeSystemMeasurables through the hooks, solver.c:1240-1259)
+    e_ref, w_ref, ns = o.spectra(u, (n, n, n))
+    e = spec.read("/Iter_00010/EnergySpectrum")
+    assert e.shape == (ns,) and np.allclose(e, e_ref[:ns], rtol=1e-10, atol=1e-12 * e_ref.max())
+    assert np.allclose(spec.read("/Iter_00010/EnstrophySpectrum"), w_ref[:ns], rtol=1e-10, atol=1e-12 * w_ref.max())
 
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(B200), reason="host/_build/solver_b200 not built (make -C host)")
 def test_reference_program_on_gpu_corrected_measures():
-    g, series, u, nw, _ = run_solver(B200, {"NSB200_CORRECT_MEASURES": "1"})
+    g, series, u, nw, _, _ = run_solver(B200, {"NSB200_CORRECT_MEASURES": "1"})
     # Taylor-Green closed forms at t = 0, which the literal sums miss (defect F4)
     assert series[0, 1] == pytest.approx(np.pi ** 3, rel=1e-12)
     assert series[0, 2] == pytest.approx(3 * np.pi ** 3, rel=1e-12)
@@ -70,11 +80,16 @@ def test_restart_from_state_file_through_the_z_flag():
     common = ["-n", n, "-n", n, "-n", n, "-h", 1e-3, "-v", 0.01, "-p", 5]
 
     def run(extra, d):
-        env = dict(os.environ, NSB_IO_STUB_DIR=d)
-        p = subprocess.run([B200] + [str(a) for a in common + extra], env=env, capture_output=True, text=True, timeout=600)
+        p = subprocess.run([B200, "-o", d + "/"] + [str(a) for a in common + extra], capture_output=True, text=True, timeout=600)
         assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
-        u = np.fromfile(os.path.join(d, "u_hat_final.bin")).view(np.complex128)
-        return u, np.loadtxt(os.path.join(d, "series.txt"))
+        import glob
+        main = h5parse.File(glob.glob(os.path.join(d, "SIM_DATA_*", "Main_HDF_Data.h5"))[0])
+        last = sorted(k for k in main.root.children if k.startswith("Iter_"))[-1]
+        u = main.read("/" + last + "/u_hat")
+        u = np.ascontiguousarray(u["r"] + 1j * u["i"])
+        u.tofile(os.path.join(d, "u_hat_final.bin"))                 # raw dump of the last saved state: what `-z` reads
+        series = np.stack([main.read("/Time"), main.read("/TotalEnergy")], axis=1)
+        return u.ravel(), series
 
     with tempfile.TemporaryDirectory() as d1, tempfile.TemporaryDirectory() as d2, tempfile.TemporaryDirectory() as d3:
         u40, s40 = run(["-s", 0.0, "-e", 0.0405, "-i", "TAYLOR_GREEN"], d1)

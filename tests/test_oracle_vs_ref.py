@@ -26,6 +26,19 @@ def test_initial_condition_and_wavenumbers(ref32):
         assert np.array_equal(a, b)
 
 
+def test_shell_spectra_pinned_by_the_reference_build(ref32):
+    """ComputeSystemMeasurables' shell binning (solver.c:1240-1259; oracle/_ref is built with -D__ENRG_SPECT -D__ENST_SPECT)."""
+    N = ref32.N
+    u = o.random_phase_ic(N, seed=11, kp=4.0)
+    ref32.set_uhat(u)
+    e, w = ref32.spectra()
+    er, wr, ns = o.spectra(u, N)
+    assert len(e) == ns == int(np.sqrt(3 * (N[0] / 2.0) ** 2)) + 1            # solver.c:1384
+    assert np.allclose(e, er[:ns], rtol=1e-13, atol=1e-15 * er.max())
+    assert np.allclose(w, wr[:ns], rtol=1e-13, atol=1e-15 * wr.max())
+    ref32.set_uhat(o.initial_condition("TAYLOR_GREEN", N))
+
+
 def test_measure_literal(ref32):
     N = ref32.N
     ref32.set_uhat(o.initial_condition("TAYLOR_GREEN", N))
