@@ -592,7 +592,7 @@ static int rk_stage(nsb200_ctx* h, int stage, double dt, int c_rs, bool in_w, cp
     }
     a.stage = stage;
     a.dealias = h->dealias;
-    a.kmax2 = h->kmax2;
+    a.kmax2 = (h->dealias == NSB200_DEALIAS_HOU_LI) ? h->N : h->kmax2;   // the Hou-Li filter needs N, not a threshold
     a.euler = (h->system == NSB200_SYSTEM_EULER);
     a.hyper2 = (h->visc_pow == 2.0);
     a.dt = dt; a.nu = h->nu; a.visc_pow = h->visc_pow;
@@ -728,7 +728,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     if (N[0] % n_ranks != 0 || (N[0] / n_ranks) % 2 != 0) return fail("nsb200_create: n_ranks must divide N with an even slab thickness");
     if (n_ranks > 1 && !nccl_unique_id) return fail("nsb200_create: nccl_unique_id required when n_ranks > 1");
     if (system != NSB200_SYSTEM_NAVIER && system != NSB200_SYSTEM_EULER) return fail("nsb200_create: bad system");
-    if (dealias_mode != NSB200_DEALIAS_NONE && dealias_mode != NSB200_DEALIAS_23) return fail("nsb200_create: bad dealias_mode");
+    if (dealias_mode != NSB200_DEALIAS_NONE && dealias_mode != NSB200_DEALIAS_23 && dealias_mode != NSB200_DEALIAS_HOU_LI) return fail("nsb200_create: bad dealias_mode");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("nsb200_create: no CUDA device available (libnsb200 has no CPU fallback)");
@@ -887,8 +887,8 @@ long nsb200_device_bytes(nsb200_ctx* h) { return h ? (long)h->bytes : 0; }
 double nsb200_link_bytes(nsb200_ctx* h) { return h ? h->link_bytes : 0.0; }
 
 // staging area (reference host layout, W[0..] is one contiguous 6-field buffer >= the 3-field host array) -> planar fields
-static int upload_staged(nsb200_ctx* h, cplx* const* dst) {
-    cplx* stage = h->W[0];
+static int upload_staged(nsb200_ctx* h, cplx* const* dst, cplx* stage = nullptr) {
+    if (!stage) stage = h->W[0];
     if (h->cyclic) {
         CKR(gpu_barrier(h));   // nobody still reads the destination arrays
         k_aos_to_planar_scatter<<<h->row_grid(), 128, 0, h->stream>>>(stage, dst[0], dst[1], dst[2], h->geom_api(), h->x_start, h->nranks, peer_table(h));
@@ -909,9 +909,9 @@ static int upload_to(nsb200_ctx* h, const double* host, cplx* const* dst) {
     return upload_staged(h, dst);
 }
 // planar fields -> staging area in the reference host layout
-static int download_stage(nsb200_ctx* h, cplx* const* src) {
+static int download_stage(nsb200_ctx* h, cplx* const* src, cplx* stage = nullptr) {
     h->curl_of = nullptr;
-    cplx* stage = h->W[0];
+    if (!stage) stage = h->W[0];
     if (h->cyclic) {
         CKR(gpu_barrier(h));   // every rank's source arrays are final
         k_planar_to_aos_gather<<<h->row_grid(), 128, 0, h->stream>>>(stage, src[0], src[1], src[2], h->geom_api(), h->x_start, h->nranks, peer_table(h));
@@ -1029,8 +1029,8 @@ int nsb200_apply_dealiasing(nsb200_ctx* h, double* array_host, int array_dim) {
     cplx* stage = h->W[0];
     h->curl_of = nullptr;
     CK(cudaMemcpyAsync(stage, array_host, n * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
-    if (h->dealias == NSB200_DEALIAS_23) {
-        k_dealias_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, array_dim, h->geom_api(), h->kmax2, h->nrows());
+    if (h->dealias != NSB200_DEALIAS_NONE) {
+        k_dealias_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, array_dim, h->geom_api(), h->kmax2, h->nrows(), h->dealias == NSB200_DEALIAS_HOU_LI);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1083,39 +1083,96 @@ int nsb200_assemble_measurables(const double p[NSB200_NMEASURE], const long N[3]
     return 0;
 }
 
+// Multi-rank non-transposed 3-D transforms (cold path: initial conditions, real-space dumps, the FFT microbenchmark).
+// Fourier side: planar fields in W[0..2] (device plane distribution); real side: the host's x slab staged in W[3..5].
+// The pipeline itself keeps real space in y slabs (one exchange per transform); the second exchange of the reference's
+// non-transposed plans is the peer gather / scatter of k_real_gather_xslab / k_real_scatter_xslab.
+static int fft3_r2c_from_yslabs(nsb200_ctx* h);
+static int fft3_c2r_multi(nsb200_ctx* h, double* stage_real, double scale) {
+    if (!h->p2p) return fail("multi-rank 3-D transforms need the peer-memory exchange (NSB200_NO_P2P is set or peer access is unavailable)");
+    h->curl_of = nullptr;
+    PassSpec yinv = {'y', INV, 'o', h->nzp, h->nzp, h->nzf, false, false, false};
+    yinv.p2p_out = true;
+    PassSpec xinv = {'x', INV, 'n', h->nzp, h->nzp, h->nzf, false, false, false};
+    CKR(gpu_barrier(h));                                   // every rank's W[0..2] is complete, nobody still reads R
+    CKR(run_pass(h, yinv, h->W, h->R, 0, 3));
+    CKR(gpu_barrier(h));
+    CKR(run_pass(h, xinv, h->R, h->R, 0, 3));
+    CKR(run_z(h, NSB_Z_C2R, 3, h->R, h->nzp, h->nzf, h->nzf));
+    CKR(gpu_barrier(h));                                   // all y slabs are in real space
+    k_real_gather_xslab<<<h->row_grid(), 128, 0, h->stream>>>(stage_real, (double*)h->R[0], (double*)h->R[1], (double*)h->R[2], h->geom_api(),
+                                                              h->x_start, h->nx_loc, h->ny_loc, scale, peer_table(h));
+    CK(cudaGetLastError());
+    h->launches++;
+    CKR(gpu_barrier(h));                                   // R may be overwritten again
+    return 0;
+}
+static int fft3_r2c_multi(nsb200_ctx* h, const double* stage_real) {
+    if (!h->p2p) return fail("multi-rank 3-D transforms need the peer-memory exchange (NSB200_NO_P2P is set or peer access is unavailable)");
+    h->curl_of = nullptr;
+    CKR(gpu_barrier(h));                                   // nobody still reads R
+    k_real_scatter_xslab<<<h->row_grid(), 128, 0, h->stream>>>(stage_real, (double*)h->R[0], (double*)h->R[1], (double*)h->R[2], h->geom_api(),
+                                                               h->x_start, h->nx_loc, h->ny_loc, peer_table(h));
+    CK(cudaGetLastError());
+    h->launches++;
+    CKR(gpu_barrier(h));                                   // every y slab has received all its x planes
+    return fft3_r2c_from_yslabs(h);
+}
+// forward transform of the real y slabs held in R[0..2]; result in W[0..2] (device plane distribution)
+static int fft3_r2c_from_yslabs(nsb200_ctx* h) {
+    CKR(run_z(h, NSB_Z_R2C, 3, h->R, h->nzp, h->nzf, h->nzf));
+    PassSpec xfwd = {'x', FWD, 'n', h->nzp, h->nzp, h->nzf, false, false, false};
+    xfwd.p2p_out = true;
+    PassSpec yfwd = {'y', FWD, 'n', h->nzp, h->nzp, h->nzf, false, false, false};
+    // the forward x pass stores into the owners' natural Fourier slabs: use R[3..5] as the receive side so that the
+    // staging area W[3..5] of ranks that are still scattering is not touched
+    CKR(run_pass(h, xfwd, h->R, h->R + 3, 0, 3));
+    CKR(gpu_barrier(h));
+    CKR(run_pass(h, yfwd, h->R + 3, h->W, 0, 3));
+    return 0;
+}
+
 int nsb200_fft_r2c(nsb200_ctx* h, const double* real_in, double* cplx_out) {
     if (!h || !real_in || !cplx_out) return fail("nsb200_fft_r2c: null argument");
-    if (h->nranks != 1) return fail("nsb200_fft_r2c: single rank only");
     CKR(set_device(h));
-    const size_t nreal = (size_t)3 * h->N * h->N * (h->N + 2);
+    const size_t nreal = (size_t)3 * h->nx_loc * h->N * (h->N + 2);
     double* stage = reinterpret_cast<double*>(h->W[3]);
     CK(cudaMemcpyAsync(stage, real_in, nreal * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    k_real_aos_to_planar<<<h->row_grid(), 128, 0, h->stream>>>(stage, (double*)h->W[0], (double*)h->W[1], (double*)h->W[2], h->geom(), h->nrows());
-    CK(cudaGetLastError());
-    h->launches++;
-    CKR(fft3_r2c_inplace(h));
-    k_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(h->W[3], h->W[0], h->W[1], h->W[2], h->geom(), h->nrows());
-    CK(cudaGetLastError());
-    h->launches++;
-    CK(cudaMemcpyAsync(cplx_out, h->W[3], (size_t)3 * h->N * h->N * h->nzf * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    if (h->nranks > 1) {
+        CKR(fft3_r2c_multi(h, stage));
+        CKR(download_stage(h, h->W, h->W[3]));
+    } else {
+        k_real_aos_to_planar<<<h->row_grid(), 128, 0, h->stream>>>(stage, (double*)h->W[0], (double*)h->W[1], (double*)h->W[2], h->geom(), h->nrows());
+        CK(cudaGetLastError());
+        h->launches++;
+        CKR(fft3_r2c_inplace(h));
+        k_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(h->W[3], h->W[0], h->W[1], h->W[2], h->geom(), h->nrows());
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    CK(cudaMemcpyAsync(cplx_out, h->W[3], (size_t)3 * h->nx_loc * h->N * h->nzf * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 int nsb200_fft_c2r(nsb200_ctx* h, const double* cplx_in, double* real_out) {
     if (!h || !cplx_in || !real_out) return fail("nsb200_fft_c2r: null argument");
-    if (h->nranks != 1) return fail("nsb200_fft_c2r: single rank only");
     CKR(set_device(h));
-    CK(cudaMemcpyAsync(h->W[3], cplx_in, (size_t)3 * h->N * h->N * h->nzf * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
-    k_aos_to_planar<<<h->row_grid(), 128, 0, h->stream>>>(h->W[3], h->W[0], h->W[1], h->W[2], h->geom(), h->nrows());
-    CK(cudaGetLastError());
-    h->launches++;
-    CKR(fft3_c2r_inplace(h));
+    CK(cudaMemcpyAsync(h->W[3], cplx_in, (size_t)3 * h->nx_loc * h->N * h->nzf * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
     double* stage = reinterpret_cast<double*>(h->W[3]);
-    k_real_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, (double*)h->W[0], (double*)h->W[1], (double*)h->W[2], h->geom(), h->nrows(), 1.0);
-    CK(cudaGetLastError());
-    h->launches++;
-    const size_t nreal = (size_t)3 * h->N * h->N * (h->N + 2);
+    if (h->nranks > 1) {
+        CKR(upload_staged(h, h->W, h->W[3]));
+        CKR(fft3_c2r_multi(h, stage, 1.0));
+    } else {
+        k_aos_to_planar<<<h->row_grid(), 128, 0, h->stream>>>(h->W[3], h->W[0], h->W[1], h->W[2], h->geom(), h->nrows());
+        CK(cudaGetLastError());
+        h->launches++;
+        CKR(fft3_c2r_inplace(h));
+        k_real_planar_to_aos<<<h->row_grid(), 128, 0, h->stream>>>(stage, (double*)h->W[0], (double*)h->W[1], (double*)h->W[2], h->geom(), h->nrows(), 1.0);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    const size_t nreal = (size_t)3 * h->nx_loc * h->N * (h->N + 2);
     CK(cudaMemcpyAsync(real_out, stage, nreal * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -1143,12 +1200,19 @@ int nsb200_download_what(nsb200_ctx* h, double* w_hat_host) {
 int nsb200_download_real(nsb200_ctx* h, int which, double* real_host) {
     if (!h || !real_host) return fail("nsb200_download_real: null argument");
     if (which != 0 && which != 1) return fail("nsb200_download_real: which must be 0 (u) or 1 (w)");
-    if (h->nranks != 1) return fail("nsb200_download_real: single rank only");
     CKR(set_device(h));
     cplx* const* src = h->U;
     if (which == 1) { CKR(curl_of_state(h)); src = h->ACC; }
     for (int d = 0; d < 3; ++d)
         CK(cudaMemcpyAsync(h->W[d], src[d], h->field_elems * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->nranks > 1) {
+        const double n3m = (double)h->N * (double)h->N * (double)h->N;
+        CKR(fft3_c2r_multi(h, reinterpret_cast<double*>(h->W[3]), 1.0 / n3m));                 // hdf5_funcs.c:588-602 / :665-679
+        const size_t nr = (size_t)3 * h->nx_loc * h->N * (h->N + 2);
+        CK(cudaMemcpyAsync(real_host, h->W[3], nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
     CKR(fft3_c2r_inplace(h));                                       // hdf5_funcs.c:588 / :665
     double* stage = reinterpret_cast<double*>(h->W[3]);
     const double n3 = (double)h->N * (double)h->N * (double)h->N;
@@ -1167,16 +1231,21 @@ int nsb200_initial_condition(nsb200_ctx* h, const char* name, unsigned long long
     CKR(set_device(h));
     const int rg = h->row_grid();
     if (!strcmp(name, "TAYLOR_GREEN") || !strcmp(name, "SHAPIRO")) {
-        if (h->nranks != 1) return fail("nsb200_initial_condition: TAYLOR_GREEN / SHAPIRO are generated on a single rank; upload the slab instead");
+        const bool multi = h->nranks > 1;
+        if (multi && !h->p2p) return fail("nsb200_initial_condition: TAYLOR_GREEN / SHAPIRO on several ranks need the peer-memory exchange");
         IcArgs a;
-        for (int d = 0; d < 3; ++d) a.r[d] = reinterpret_cast<double*>(h->W[d]);
+        // real space lives in y slabs on the device (every rank fills its own rows); one rank: W, in place
+        for (int d = 0; d < 3; ++d) a.r[d] = reinterpret_cast<double*>(multi ? h->R[d] : h->W[d]);
         a.g = h->geom();
         a.kind = !strcmp(name, "SHAPIRO");
         a.nu = h->nu;
+        a.y0 = h->rank * h->ny_loc; a.ny_loc = h->ny_loc;
+        if (multi) CKR(gpu_barrier(h));                             // nobody still reads R
         k_ic_real<<<rg, 128, 0, h->stream>>>(a);
         CK(cudaGetLastError());
         h->launches++;
-        CKR(fft3_r2c_inplace(h));                                   // solver.c:1573 / :1599
+        if (multi) CKR(fft3_r2c_from_yslabs(h));
+        else CKR(fft3_r2c_inplace(h));                              // solver.c:1573 / :1599
         for (int d = 0; d < 3; ++d)
             CK(cudaMemcpyAsync(h->U[d], h->W[d], h->field_elems * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
     } else if (!strcmp(name, "RANDOM_PHASE")) {
@@ -1189,8 +1258,8 @@ int nsb200_initial_condition(nsb200_ctx* h, const char* name, unsigned long long
     } else {
         return fail(std::string("nsb200_initial_condition: unknown initial condition '") + name + "'");
     }
-    if (h->dealias == NSB200_DEALIAS_23) {                          // solver.c:1630
-        k_dealias_planar<<<rg, 128, 0, h->stream>>>(h->U[0], h->U[1], h->U[2], h->geom(), h->kmax2);
+    if (h->dealias != NSB200_DEALIAS_NONE) {                        // solver.c:1630
+        k_dealias_planar<<<rg, 128, 0, h->stream>>>(h->U[0], h->U[1], h->U[2], h->geom(), h->kmax2, h->dealias == NSB200_DEALIAS_HOU_LI);
         CK(cudaGetLastError());
         h->launches++;
     }

@@ -168,6 +168,54 @@ __global__ void k_real_planar_to_aos(double* __restrict__ aos, const double* p0,
     }
 }
 
+// Multi-GPU real-space boundary (the reference's non-transposed batch plans, solver.c:2056-2057): the host holds x slabs
+// [local_Nx][Ny][Nz+2][3] while the device pipeline keeps real space in y slabs [x][y_loc][2*nzp] (one exchange per
+// transform).  These two kernels are the second "transpose" of the non-transposed plans, done over peer
+// memory: gather this rank's x slab from every y-slab owner, or scatter it to them.
+__global__ void k_real_gather_xslab(double* __restrict__ aos, const double* r0, const double* r1, const double* r2, Geom g, int x0,
+                                    int nx_loc, int ny_loc, double scale, PeerTable pt) {
+    __shared__ long long s_delta[NSB_MAX_PEERS];
+    if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = pt.delta[threadIdx.x];
+    __syncthreads();
+    const long long nrows = (long long)nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), y = (int)(row % g.N);
+        const int owner = y / ny_loc, yl = y % ny_loc;
+        const long long srow = ((long long)(x0 + i) * ny_loc + yl) * 2 * g.nzp;
+        const double* s0 = reinterpret_cast<const double*>(reinterpret_cast<const char*>(r0) + s_delta[owner]) + srow;
+        const double* s1 = reinterpret_cast<const double*>(reinterpret_cast<const char*>(r1) + s_delta[owner]) + srow;
+        const double* s2 = reinterpret_cast<const double*>(reinterpret_cast<const char*>(r2) + s_delta[owner]) + srow;
+        double* dst = aos + row * (g.N + 2) * 3;
+        for (int k = threadIdx.x; k < g.N + 2; k += blockDim.x) {
+            const bool in = k < g.N;
+            dst[3 * k + 0] = in ? s0[k] * scale : 0.0;
+            dst[3 * k + 1] = in ? s1[k] * scale : 0.0;
+            dst[3 * k + 2] = in ? s2[k] * scale : 0.0;
+        }
+    }
+}
+__global__ void k_real_scatter_xslab(const double* __restrict__ aos, double* r0, double* r1, double* r2, Geom g, int x0, int nx_loc,
+                                     int ny_loc, PeerTable pt) {
+    __shared__ long long s_delta[NSB_MAX_PEERS];
+    if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = pt.delta[threadIdx.x];
+    __syncthreads();
+    const long long nrows = (long long)nx_loc * g.N;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int i = (int)(row / g.N), y = (int)(row % g.N);
+        const int owner = y / ny_loc, yl = y % ny_loc;
+        const long long drow = ((long long)(x0 + i) * ny_loc + yl) * 2 * g.nzp;
+        double* d0 = reinterpret_cast<double*>(reinterpret_cast<char*>(r0) + s_delta[owner]) + drow;
+        double* d1 = reinterpret_cast<double*>(reinterpret_cast<char*>(r1) + s_delta[owner]) + drow;
+        double* d2 = reinterpret_cast<double*>(reinterpret_cast<char*>(r2) + s_delta[owner]) + drow;
+        const double* src = aos + row * (g.N + 2) * 3;
+        for (int k = threadIdx.x; k < g.N; k += blockDim.x) {
+            d0[k] = src[3 * k + 0];
+            d1[k] = src[3 * k + 1];
+            d2[k] = src[3 * k + 2];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ spectral curl
 struct CurlArgs {
     const cplx* u[3];
@@ -224,7 +272,16 @@ struct RkArgs {
 #define NSB_RK4_B3 (1.0 / 3.0)
 #define NSB_RK4_B4 (1.0 / 6.0)
 
-// solver.c:697-718 then :1732-1737 for one mode
+// Hou-Li filter exp(-36 (|k / (N/2)|)^36) (solver.c:1744-1751).  That branch of the reference is dead code
+// (__DEALIAS_23 is hard-defined, data_types.h:63) and does not compile as written (`Nz` is undeclared; its k / (N/2) are
+// integer divisions); the filter of Hou & Li (2007) it names, with real-valued division, is implemented here.
+NSB_HD double nsb_hou_li(int kx, int ky, int kz, int N) {
+    const double h = 0.5 * (double)N;
+    const double a = (double)kx / h, b = (double)ky / h, c = (double)kz / h;
+    return exp(-36.0 * pow(sqrt(a * a + b * b + c * c), 36.0));
+}
+
+// solver.c:697-718 then :1732-1737 (dealias == 1) or :1744-1751 (dealias == 2) for one mode; kmax2 carries N when dealias == 2
 NSB_HD void project_mode(int kx, int ky, int kz, double norm, int dealias, int kmax2, cplx& c0, cplx& c1, cplx& c2) {
     c0 = rmul(norm, c0); c1 = rmul(norm, c1); c2 = rmul(norm, c2);
     const int k2 = kx * kx + ky * ky + kz * kz;
@@ -237,7 +294,11 @@ NSB_HD void project_mode(int kx, int ky, int kz, double norm, int dealias, int k
     } else {
         c0 = c1 = c2 = mk(0.0, 0.0);
     }
-    if (dealias && k2 > kmax2) c0 = c1 = c2 = mk(0.0, 0.0);
+    if (dealias == 1 && k2 > kmax2) c0 = c1 = c2 = mk(0.0, 0.0);
+    if (dealias == 2) {
+        const double f = nsb_hou_li(kx, ky, kz, kmax2);
+        c0 = rmul(f, c0); c1 = rmul(f, c1); c2 = rmul(f, c2);
+    }
 }
 
 __global__ void k_rk_stage(const RkArgs a) {
@@ -317,26 +378,34 @@ __global__ void k_rk_stage(const RkArgs a) {
 }
 
 // ------------------------------------------------------------------------------ ApplyDealiasing on the host layout
-__global__ void k_dealias_aos(cplx* arr, int dim, Geom g, int kmax2, long long nrows) {
+__global__ void k_dealias_aos(cplx* arr, int dim, Geom g, int kmax2, long long nrows, int hou_li) {
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
         const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
-            if (kx * kx + ky * ky + k * k > kmax2)
+            if (hou_li) {
+                const double f = nsb_hou_li(kx, ky, k, g.N);
+                for (int l = 0; l < dim; ++l) arr[(row * g.nzf + k) * dim + l] = rmul(f, arr[(row * g.nzf + k) * dim + l]);
+            } else if (kx * kx + ky * ky + k * k > kmax2) {
                 for (int l = 0; l < dim; ++l) arr[(row * g.nzf + k) * dim + l] = mk(0.0, 0.0);
+            }
         }
     }
 }
-__global__ void k_dealias_planar(cplx* p0, cplx* p1, cplx* p2, Geom g, int kmax2) {
+__global__ void k_dealias_planar(cplx* p0, cplx* p1, cplx* p2, Geom g, int kmax2, int hou_li) {
     const long long nrows = (long long)g.nx_loc * g.N;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
         const int i = (int)(row / g.N), j = (int)(row % g.N);
         const int kx = nsb_wavenum(g.x_start + i * g.x_stride, g.N), ky = nsb_wavenum(j, g.N);
         for (int k = threadIdx.x; k < g.nzf; k += blockDim.x) {
-            if (kx * kx + ky * ky + k * k > kmax2) {
-                p0[row * g.nzp + k] = mk(0.0, 0.0);
-                p1[row * g.nzp + k] = mk(0.0, 0.0);
-                p2[row * g.nzp + k] = mk(0.0, 0.0);
+            const long long e = row * g.nzp + k;
+            if (hou_li) {
+                const double f = nsb_hou_li(kx, ky, k, g.N);
+                p0[e] = rmul(f, p0[e]); p1[e] = rmul(f, p1[e]); p2[e] = rmul(f, p2[e]);
+            } else if (kx * kx + ky * ky + k * k > kmax2) {
+                p0[e] = mk(0.0, 0.0);
+                p1[e] = mk(0.0, 0.0);
+                p2[e] = mk(0.0, 0.0);
             }
         }
     }
@@ -488,13 +557,14 @@ struct IcArgs {
     Geom g;
     int kind;   // 0 Taylor-Green, 1 Shapiro
     double nu;
+    int y0, ny_loc;   // this rank's y slab of the real layout [x][y_loc][z]
 };
 __global__ void k_ic_real(const IcArgs a) {
     const Geom g = a.g;
-    const long long nrows = (long long)g.N * g.N;   // single-GPU real layout [x][y][z]
+    const long long nrows = (long long)g.N * a.ny_loc;
     const double dx = 2.0 * 3.14159265358979323846 / (double)g.N;
     for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const int i = (int)(row / g.N), j = (int)(row % g.N);
+        const int i = (int)(row / a.ny_loc), j = a.y0 + (int)(row % a.ny_loc);
         const double x = (double)i * dx, y = (double)j * dx;
         for (int k = threadIdx.x; k < g.N; k += blockDim.x) {
             const double z = (double)k * dx;

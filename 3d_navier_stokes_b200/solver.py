@@ -30,7 +30,7 @@ class Solver:
         if nccl_unique_id is not None:
             uid = ctypes.create_string_buffer(bytes(nccl_unique_id), 128)
         rc = self.lib.nsb200_create(ctypes.byref(h), Narr, int(device), self.nu, self.visc_pow,
-                                    0 if system == "NAVIER" else 1, 1 if dealias else 0,
+                                    0 if system == "NAVIER" else 1, 2 if dealias == "HOU_LI" else (1 if dealias else 0),
                                     self.rank, self.n_ranks, uid)
         self.lib.check(rc, "nsb200_create")
         self.h = h

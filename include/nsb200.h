@@ -30,6 +30,8 @@ typedef struct nsb200_ctx nsb200_ctx;
 
 #define NSB200_DEALIAS_NONE 0
 #define NSB200_DEALIAS_23 1 /* spherical 2/3 rule, integer threshold Nx/3 (solver.c:1732) */
+#define NSB200_DEALIAS_HOU_LI 2 /* exp(-36 |k/(N/2)|^36) (solver.c:1744-1751: dead, non-compiling code in the reference; the
+                                   filter it names is implemented with real-valued division).  No sharp support: full transforms. */
 
 #define NSB200_SYSTEM_NAVIER 0 /* -D__NAVIER: viscous factor in the final update (solver.c:588-603) */
 #define NSB200_SYSTEM_EULER 1  /* -D__EULER  (solver.c:583-587) */

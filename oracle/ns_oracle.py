@@ -85,9 +85,22 @@ def dealias_mask(N, local_start=0, local_n=None):
     return ksqr_int(N, local_start, local_n) <= kmax * kmax
 
 
-def apply_dealiasing(arr, N, local_start=0, local_n=None):
+def hou_li_filter(N, local_start=0, local_n=None):
+    """exp(-36 |k/(N/2)|^36), solver.c:1744-1751.  That branch is dead in the reference (__DEALIAS_23 is forced,
+    data_types.h:63) and does not compile as written (undeclared Nz, integer divisions); this is the filter of
+    Hou & Li (2007) it names, the semantics of the ABI's NSB200_DEALIAS_HOU_LI mode."""
+    kx, ky, kz = wavenumbers(N, local_start, local_n)
+    a = (kx / (N[0] / 2.0))[:, None, None]
+    b = (ky / (N[1] / 2.0))[None, :, None]
+    c = (kz / (N[2] / 2.0))[None, None, :]
+    return np.exp(-36.0 * np.sqrt(a * a + b * b + c * c) ** 36.0)
+
+
+def apply_dealiasing(arr, N, local_start=0, local_n=None, mode=True):
     """ApplyDealiasing (solver.c:1709-1756) with F2: kept modes untouched."""
     out = arr.copy()
+    if isinstance(mode, str) and mode == "HOU_LI":
+        return out * hou_li_filter(N, local_start, local_n).reshape(out.shape[:3] + (1,) * (out.ndim - 3))
     out[~dealias_mask(N, local_start, local_n)] = 0.0
     return out
 
@@ -254,7 +267,7 @@ def nonlinear_rhs(u_hat, N, dealias=True):
     out[..., 1] -= KY * k2inv * kdot
     out[..., 2] -= KZ * k2inv * kdot
     out[0, 0, 0, :] = 0.0                             # :713-718
-    return apply_dealiasing(out, N) if dealias else out   # :727 (dealias=False: the ABI's NSB200_DEALIAS_NONE mode)
+    return apply_dealiasing(out, N, mode=dealias) if dealias else out   # :727 (dealias=False: the ABI's NSB200_DEALIAS_NONE mode)
 
 
 # --------------------------------------------------------------------------------------

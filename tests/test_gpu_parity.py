@@ -172,6 +172,22 @@ def test_dealias_none_mode_and_undealiased_input():
         assert rel(s.get_u_hat(), o.rk4_step(u, N, dt, 0.02)) < TOL_FIELD
 
 
+def test_hou_li_dealias_variant():
+    """the Hou-Li filter (solver.c:1744-1751, dead code in the reference) as dealias mode 2: no sharp
+    support, so the full (unpruned) transforms run; filter values come from exp/pow, hence 1e-12 rather than bit exact."""
+    n = 32; N = (n, n, n); dt = 1e-3
+    rng = np.random.default_rng(7)
+    u = o.random_phase_ic(N, seed=5, kp=6.0)
+    with nsb.Solver(n, nu=0.02, dealias="HOU_LI") as s:
+        a = rng.standard_normal(s.shape_f) + 1j * rng.standard_normal(s.shape_f)
+        assert rel(s.apply_dealiasing(a), o.apply_dealiasing(a, N, mode="HOU_LI")) < 1e-14
+        assert rel(s.nonlinear_rhs_batch(u), o.nonlinear_rhs(u, N, dealias="HOU_LI")) < TOL_FIELD
+        s.set_u_hat(u)
+        s.rk4_step(dt, n_steps=2)
+        ref = o.rk4_step(o.rk4_step(u, N, dt, 0.02, dealias="HOU_LI"), N, dt, 0.02, dealias="HOU_LI")
+        assert rel(s.get_u_hat(), ref) < TOL_FIELD
+
+
 def test_input_is_preserved_like_fftw_preserve_input():
     n = 32; N = (n, n, n)
     u0 = o.random_phase_ic(N, seed=9, kp=4.0)

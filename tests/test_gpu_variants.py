@@ -76,3 +76,16 @@ def test_two_ranks_match_one_rank():
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert p.stdout.count(" OK") >= 6
+
+
+def test_two_ranks_transform_api_and_real_dumps():
+    """Multi-rank non-transposed r2c / c2r (solver.c:2056-2057), real-space dumps (hdf5_funcs.c:586-697) and the real-space
+    initial conditions, against the restatement on every rank (scripts/mgpu_fft_check.py)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29534", os.path.join(ROOT, "scripts", "mgpu_fft_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert p.stdout.count(" OK") >= 4
