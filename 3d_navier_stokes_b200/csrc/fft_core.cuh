@@ -364,6 +364,32 @@ template <int DIR> NSB_HD void twiddle8_base(cplx* v, cplx wa, cplx wb, cplx wc)
     v[6] = cmul_dir<DIR>(v[6], cmul(wb, wc));
 }
 
+// radix-16 mid pass with the fifteen twiddle powers formed on the fly from W^1, W^2, W^4, W^8 (16 registers instead of 60)
+template <int DIR> NSB_HD void twiddle16_base(cplx* v, cplx w1, cplx w2, cplx w4, cplx w8) {
+    const cplx w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4);
+    const cplx w7 = cmul(w3, w4);
+    v[1] = cmul_dir<DIR>(v[1], w1);   v[2] = cmul_dir<DIR>(v[2], w2);   v[3] = cmul_dir<DIR>(v[3], w3);
+    v[4] = cmul_dir<DIR>(v[4], w4);   v[5] = cmul_dir<DIR>(v[5], w5);   v[6] = cmul_dir<DIR>(v[6], w6);
+    v[7] = cmul_dir<DIR>(v[7], w7);   v[8] = cmul_dir<DIR>(v[8], w8);
+    v[9] = cmul_dir<DIR>(v[9], cmul(w1, w8));    v[10] = cmul_dir<DIR>(v[10], cmul(w2, w8));
+    v[11] = cmul_dir<DIR>(v[11], cmul(w3, w8));  v[12] = cmul_dir<DIR>(v[12], cmul(w4, w8));
+    v[13] = cmul_dir<DIR>(v[13], cmul(w5, w8));  v[14] = cmul_dir<DIR>(v[14], cmul(w6, w8));
+    v[15] = cmul_dir<DIR>(v[15], cmul(w7, w8));
+}
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass2_r16_base(int b, cplx* sm, cplx w1, cplx w2, cplx w4, cplx w8) {
+    static_assert(P::PASSES >= 3 && P::R2 == 16, "radix-16 pass 2");
+    const int k1 = b / P::M2, m2 = b % P::M2;
+    const int base = k1 * P::ROW + m2;
+    cplx v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = sm[(base + j * P::M2) * STRIDE];
+    Dft<16, DIR>::run(v);
+    twiddle16_base<DIR>(v, w1, w2, w4, w8);
+#pragma unroll
+    for (int kp = 0; kp < 16; ++kp) sm[(base + kp * P::M2) * STRIDE] = v[kp];
+}
+
 // start of the RL contiguous elements the last pass of butterfly b works on (b = k1 + R1*k1' [+ R1*R2*k1''])
 template <class P> NSB_HD int fft_row_base(int b) {
     if constexpr (P::PASSES == 4) {

@@ -15,11 +15,20 @@
 #else
 #define NSB_HAVE_ZFW 0
 #endif
+// ... and in its general form (two mirrored pairs per lane, radix-16 middle pass) for 1024 = 8 x 16 x 8
+#if NSB_N == 1024
+#define NSB_HAVE_ZG 1
+#else
+#define NSB_HAVE_ZG 0
+#endif
 
 namespace {
 typedef BigPlan<NSB_N>::type BP;
 typedef ZPlan<NSB_N>::type ZP;
 typedef ZFPlan<NSB_N>::type ZF;
+#if NSB_HAVE_ZG
+typedef FftPlan<NSB_N, 8, 16, 8> ZG;
+#endif
 constexpr int ST = StridedCfg<NSB_N>::T, STP = StridedCfg<NSB_N>::TP;
 constexpr size_t kStridedSmem = (size_t)BP::NPAD * ST * sizeof(cplx);
 constexpr size_t kZSmem = (size_t)ZP::NPAD * ZCfg<ZP>::G * sizeof(cplx);
@@ -45,6 +54,18 @@ int setup() {
     if (e != cudaSuccess) return (int)e;
 #if NSB_HAVE_ZFW
     e = cudaFuncSetAttribute(k_z_fused_w<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpCfg<ZF>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_z_c2r_w<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpPassCfg<ZF>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_z_r2c_w<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpPassCfg<ZF>::SMEM);
+#endif
+#if NSB_HAVE_ZG
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_zg_fused<ZG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZGenCfg<ZG>::FUSED_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_zg_c2r<ZG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZGenCfg<ZG>::PASS_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_zg_r2c<ZG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZGenCfg<ZG>::PASS_SMEM);
 #endif
     return (int)e;
 }
@@ -137,6 +158,13 @@ int zlaunch(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s) 
     else if (which == NSB_Z_R2C) k_z_r2c<ZP><<<dim3(grid_x, nfields), TH, kZSmem, s>>>(*a);
 #if NSB_HAVE_ZFW
     else if (which == NSB_Z_FUSED_W) k_z_fused_w<ZF><<<dim3(grid_x), ZWarpCfg<ZF>::THREADS, ZWarpCfg<ZF>::SMEM, s>>>(*a);
+    else if (which == NSB_Z_C2R_W) k_z_c2r_w<ZF><<<dim3(grid_x, nfields), ZWarpPassCfg<ZF>::THREADS, ZWarpPassCfg<ZF>::SMEM, s>>>(*a);
+    else if (which == NSB_Z_R2C_W) k_z_r2c_w<ZF><<<dim3(grid_x, nfields), ZWarpPassCfg<ZF>::THREADS, ZWarpPassCfg<ZF>::SMEM, s>>>(*a);
+#endif
+#if NSB_HAVE_ZG
+    else if (which == NSB_Z_FUSED_W) k_zg_fused<ZG><<<dim3(grid_x), ZGenCfg<ZG>::FUSED_THREADS, ZGenCfg<ZG>::FUSED_SMEM, s>>>(*a);
+    else if (which == NSB_Z_C2R_W) k_zg_c2r<ZG><<<dim3(grid_x, nfields), ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM, s>>>(*a);
+    else if (which == NSB_Z_R2C_W) k_zg_r2c<ZG><<<dim3(grid_x, nfields), ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM, s>>>(*a);
 #endif
     else k_z_fused<ZF><<<dim3(grid_x), ZFusedCfg<ZF>::THREADS, kZFusedSmem, s>>>(*a);
     return (int)cudaGetLastError();
@@ -149,10 +177,20 @@ int zocc(int which) {
     else if (which == NSB_Z_R2C) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_r2c<ZP>, TH, kZSmem);
 #if NSB_HAVE_ZFW
     else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused_w<ZF>, ZWarpCfg<ZF>::THREADS, ZWarpCfg<ZF>::SMEM);
+    else if (which == NSB_Z_C2R_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_c2r_w<ZF>, ZWarpPassCfg<ZF>::THREADS, ZWarpPassCfg<ZF>::SMEM);
+    else if (which == NSB_Z_R2C_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_r2c_w<ZF>, ZWarpPassCfg<ZF>::THREADS, ZWarpPassCfg<ZF>::SMEM);
+#endif
+#if NSB_HAVE_ZG
+    else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zg_fused<ZG>, ZGenCfg<ZG>::FUSED_THREADS, ZGenCfg<ZG>::FUSED_SMEM);
+    else if (which == NSB_Z_C2R_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zg_c2r<ZG>, ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM);
+    else if (which == NSB_Z_R2C_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zg_r2c<ZG>, ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM);
 #endif
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused<ZF>, ZFusedCfg<ZF>::THREADS, kZFusedSmem);
     return n;
 }
 }  // namespace
 
-extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, NSB_PIPE_TCOLS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G, NSB_HAVE_ZFW}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC, NSB_RING_FN};
+extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, NSB_PIPE_TCOLS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G,
+     // 1024: the general fused kernel (249 registers, 2 x 3 warps per SM) measured slower than the first generation (117.5 vs 108.8 ms
+     // per step), the stand-alone passes faster (65 vs 56 % of the HBM peak): NSB200_ZF=warp still selects it for experiments
+     NSB_HAVE_ZFW ? 1 : (NSB_HAVE_ZG ? -1 : 0), (NSB_HAVE_ZFW || NSB_HAVE_ZG) ? 4 : 0, (NSB_HAVE_ZFW || NSB_HAVE_ZG) ? 4 : 0}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC, NSB_RING_FN};

@@ -3,14 +3,14 @@
 #pragma once
 #include "fft_kernels.cuh"
 
-enum { NSB_Z_C2R = 0, NSB_Z_R2C = 1, NSB_Z_FUSED = 2, NSB_Z_FUSED_W = 3, NSB_Z_KINDS = 4 };
+enum { NSB_Z_C2R = 0, NSB_Z_R2C = 1, NSB_Z_FUSED = 2, NSB_Z_FUSED_W = 3, NSB_Z_C2R_W = 4, NSB_Z_R2C_W = 5, NSB_Z_KINDS = 6 };
 
 struct FftOps {
     int N;
     int strided_T;                 // kz columns per strided tile
     int tma_rows;                  // rows per TMA box of the strided tile load
     int pipe_T;                    // kz columns per tile of the persistent strided pass (0: not built)
-    int z_pairs_per_cta[NSB_Z_KINDS];   // row pairs per CTA for NSB_Z_C2R / _R2C / _FUSED / _FUSED_W (0: kernel not built for this N)
+    int z_pairs_per_cta[NSB_Z_KINDS];   // row pairs per CTA for NSB_Z_C2R / _R2C / _FUSED and their warp-per-transform versions (0: kernel not built for this N)
     int (*setup)(void);            // opt-in to large dynamic shared memory; returns cudaError_t
     // one c2c pass over `nfields` fields; grid = (ceil(nzv/T), n_outer_eff, nfields)
     // maps != NULL: tile loads through TMA tensor maps (natural layouts); NULL: cp.async path

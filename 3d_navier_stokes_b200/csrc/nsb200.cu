@@ -180,11 +180,14 @@ struct nsb200_ctx {
     int* bar_dev = nullptr;
     unsigned* flags = nullptr;                     // barrier flag page at the end of the slab (peer mapped with it)
     unsigned epoch[NSB_BARRIER_SLOTS] = {0};
+    unsigned barrier_spins = 1u << 27;             // polls of the peer flag before a rank gives up on its peers (about a minute;
+                                                   // NSB200_BARRIER_SPINS overrides, e.g. under a debugger or with long host-side skew)
     bool overlap = false;                          // two-stream schedule of the fused exchange: on for >= 4 ranks, where it was
                                                    // measured faster (NSB200_OVERLAP=0/1 overrides); needs link_ctas > 0 to pay
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     int sm_count = 0;
-    int zgrid[NSB_Z_KINDS] = {0, 0, 0, 0};
+    int zgrid[NSB_Z_KINDS] = {0, 0, 0, 0, 0, 0};
+    bool z_warp_passes = false;    // stand-alone z passes: warp-per-transform kernels where built
     int zf_kind = NSB_Z_FUSED;     // NSB_Z_FUSED_W (one warp per transform) where built; NSB200_ZF=old keeps the first generation
     long launches = 0;
     double link_bytes = 0.0;       // bytes this rank has stored into peer memory (the fused slab exchange)
@@ -386,16 +389,18 @@ static int run_z(nsb200_ctx* h, int which, int nfields, cplx* const* f, int rs, 
     a.kz_in = kz_in;
     a.kz_out = kz_out;
     const bool fused = (which == NSB_Z_FUSED);
+    const int cls = which;                           // profile class of the caller's request
     if (fused) which = h->zf_kind;
-    const int gpc = h->ops->z_pairs_per_cta[which];
+    else if (h->z_warp_passes) which = (which == NSB_Z_C2R) ? NSB_Z_C2R_W : NSB_Z_R2C_W;
+    const int gpc = abs(h->ops->z_pairs_per_cta[which]);
     long long want = (a.npairs + gpc - 1) / gpc;
     int grid = (int)(want < h->zgrid[which] ? want : h->zgrid[which]);
     {
         const double rows = 2.0 * (double)a.npairs;
         const double bytes = fused ? rows * 16.0 * (6.0 * kz_in + 3.0 * kz_out)
-                           : which == NSB_Z_C2R ? nfields * rows * (16.0 * kz_in + 8.0 * h->N)
+                           : cls == NSB_Z_C2R ? nfields * rows * (16.0 * kz_in + 8.0 * h->N)
                                                 : nfields * rows * (8.0 * h->N + 16.0 * kz_out);
-        ProfScope ps(h, fused ? NSB200_PC_Z_FUSED : which == NSB_Z_C2R ? NSB200_PC_Z_C2R : NSB200_PC_Z_R2C, bytes);
+        ProfScope ps(h, fused ? NSB200_PC_Z_FUSED : cls == NSB_Z_C2R ? NSB200_PC_Z_C2R : NSB200_PC_Z_R2C, bytes);
         CKI(h->ops->z(which, &a, nfields, grid, h->stream));
     }
     h->launches++;
@@ -425,7 +430,7 @@ static PeerTable peer_table(const nsb200_ctx* h) {
 static int gpu_barrier(nsb200_ctx* h, cudaStream_t st = nullptr, int slot = 0) {
     if (!st) st = h->stream;
     if (h->p2p) {   // flag barrier over peer memory (a few microseconds)
-        k_gpu_barrier<<<1, 32, 0, st>>>(h->flags, peer_table(h), h->rank, h->nranks, slot, ++h->epoch[slot]);
+        k_gpu_barrier<<<1, 32, 0, st>>>(h->flags, peer_table(h), h->rank, h->nranks, slot, ++h->epoch[slot], h->barrier_spins);
         CK(cudaGetLastError());
         h->launches++;
         return 0;
@@ -604,7 +609,9 @@ static int rk_stage(nsb200_ctx* h, int stage, double dt, int c_rs, bool in_w, cp
         const double nc = out_w ? (2.0 * h->kmax + 1) * (2.0 * h->kmax + 1) * (h->kmax + 1) / h->nranks : (double)h->nrows() * h->nzf;
         const double arrays = (stage == 0 ? 9.0 : stage == 3 ? 9.0 : stage == 4 ? 3.0 : 12.0) + (a.w[0] ? 3.0 : 0.0);   // besides c: u, acc, tmp (, w)
         ProfScope ps(h, NSB200_PC_RK, 16.0 * (3.0 * nc + arrays * (kw * kw / h->nranks) * nk));
-        k_rk_stage<<<h->row_grid(), nsb200_ctx::row_block(a.skip_outside ? h->kmax + 1 : h->nzf), 0, h->stream>>>(a);
+        const dim3 grid(h->row_grid()), block(nsb200_ctx::row_block(a.skip_outside ? h->kmax + 1 : h->nzf));
+        if (h->dealias == NSB200_DEALIAS_HOU_LI) k_rk_stage<true><<<grid, block, 0, h->stream>>>(a);
+        else k_rk_stage<false><<<grid, block, 0, h->stream>>>(a);
     }
     CK(cudaGetLastError());
     h->launches++;
@@ -745,12 +752,19 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     { const char* e = getenv("NSB200_NO_PRUNE"); h->prune = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_NO_TMA"); h->use_tma = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_NO_FUSE_CURL"); h->fuse_curl = !(e && e[0] == '1'); }
+    { const char* e = getenv("NSB200_BARRIER_SPINS"); if (e && atof(e) >= 1024.0) h->barrier_spins = (unsigned)std::min(atof(e), 4.0e9); }
     { const char* e = getenv("NSB200_PIPE"); h->use_pipe = (e && e[0] == '1'); }
     { const char* e = getenv("NSB200_RING"); h->use_ring = !(e && e[0] == '0') && !h->use_pipe; }
     h->link_ctas = (h->nranks >= 8) ? 128 : 96;   // measured: 4 ranks 11.22 -> 10.58 ms (96), 8 ranks 6.26 -> 6.02 ms (128)
     { const char* e = getenv("NSB200_LINK_CTAS"); if (e) h->link_ctas = atoi(e); }
     h->ops = ops;
-    { const char* e = getenv("NSB200_ZF"); if (ops->z_pairs_per_cta[NSB_Z_FUSED_W] > 0 && !(e && !strcmp(e, "old"))) h->zf_kind = NSB_Z_FUSED_W; }
+    {   // z kernels: warp-per-transform generation where built (z_pairs_per_cta > 0: default; < 0: built but not the default)
+        const char* e = getenv("NSB200_ZF");
+        const bool old = e && !strcmp(e, "old"), force = e && !strcmp(e, "warp");
+        const int fw = ops->z_pairs_per_cta[NSB_Z_FUSED_W];
+        if (!old && (fw > 0 || (fw < 0 && force))) h->zf_kind = NSB_Z_FUSED_W;
+        h->z_warp_passes = !old && ops->z_pairs_per_cta[NSB_Z_C2R_W] > 0;
+    }
     h->field_elems = (size_t)h->nx_loc * h->N * h->nzp;
 #define CKC(call)                                                                                    \
     do {                                                                                             \
@@ -1347,14 +1361,34 @@ int nsb200_time_op(nsb200_ctx* h, int op, int iters, double dt, double* elapsed_
         CK(cudaMalloc(&h->flush_buf, h->flush_bytes));
         h->bytes += h->flush_bytes;
     }
-    if (op != NSB200_OP_RK4_STEP && op != NSB200_OP_L2_FLUSH && op != NSB200_OP_RK_POINTWISE && h->nranks != 1)
+    const bool multi_fft = (op == NSB200_OP_FFT_C2R_R2C && h->nranks > 1 && h->p2p);
+    if (op != NSB200_OP_RK4_STEP && op != NSB200_OP_L2_FLUSH && op != NSB200_OP_RK_POINTWISE && h->nranks != 1 && !multi_fft)
         return fail("nsb200_time_op: single-pass timings are single rank only");
+    if (multi_fft) CKR(gpu_barrier(h));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
     for (int it = 0; it < iters; ++it) {
         switch (op) {
             case NSB200_OP_RK4_STEP: CKR(step(h, dt)); break;
-            case NSB200_OP_FFT_C2R_R2C: CKR(fft3_c2r_inplace(h)); CKR(fft3_r2c_inplace(h)); break;
+            case NSB200_OP_FFT_C2R_R2C:
+                if (multi_fft) {
+                    // the transposed pair the solver uses (one slab exchange per transform), full spectrum, 3 fields:
+                    // W -> y inverse + exchange -> R: x inverse, z c2r | z r2c, x forward + exchange -> R[3..5] -> y forward -> W
+                    PassSpec yinv = {'y', INV, 'o', h->nzp, h->nzp, h->nzf, false, false, false};
+                    PassSpec xinv = {'x', INV, 'n', h->nzp, h->nzp, h->nzf, false, false, false};
+                    PassSpec xfwd = {'x', FWD, 'n', h->nzp, h->nzp, h->nzf, false, false, false};
+                    PassSpec yfwd = {'y', FWD, 'n', h->nzp, h->nzp, h->nzf, false, false, false};
+                    yinv.p2p_out = xfwd.p2p_out = true;
+                    CKR(run_pass(h, yinv, h->W, h->R, 0, 3));
+                    CKR(gpu_barrier(h));
+                    CKR(run_pass(h, xinv, h->R, h->R, 0, 3));
+                    CKR(run_z(h, NSB_Z_C2R, 3, h->R, h->nzp, h->nzf, h->nzf));
+                    CKR(run_z(h, NSB_Z_R2C, 3, h->R, h->nzp, h->nzf, h->nzf));
+                    CKR(run_pass(h, xfwd, h->R, h->R + 3, 0, 3));
+                    CKR(gpu_barrier(h));
+                    CKR(run_pass(h, yfwd, h->R + 3, h->W, 0, 3));
+                } else { CKR(fft3_c2r_inplace(h)); CKR(fft3_r2c_inplace(h)); }
+                break;
             case NSB200_OP_PASS_Y: CKR(run_pass_full(h, 'y', INV, 3, h->W, h->W)); break;
             case NSB200_OP_PASS_X: CKR(run_pass_full(h, 'x', INV, 3, h->W, h->W)); break;
             case NSB200_OP_PASS_Z: CKR(run_z(h, NSB_Z_C2R, 3, h->W, h->nzp, h->nzf, h->nzf)); break;

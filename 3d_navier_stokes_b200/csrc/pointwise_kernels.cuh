@@ -127,7 +127,7 @@ __global__ void k_planar_to_aos_gather(cplx* __restrict__ aos, const cplx* p0, c
 // waits until all peers' epochs have arrived in its own page.  Kernel boundaries order it against the FFT kernels
 // whose peer stores it publishes; bounded spin so that a lost peer traps instead of hanging the GPU.
 #define NSB_BARRIER_SLOTS 8
-__global__ void k_gpu_barrier(unsigned* flags, PeerTable pt, int rank, int nranks, int slot, unsigned epoch) {
+__global__ void k_gpu_barrier(unsigned* flags, PeerTable pt, int rank, int nranks, int slot, unsigned epoch, unsigned max_spins) {
     __shared__ long long s_delta[NSB_MAX_PEERS];
     if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = pt.delta[threadIdx.x];
     __syncthreads();
@@ -139,7 +139,7 @@ __global__ void k_gpu_barrier(unsigned* flags, PeerTable pt, int rank, int nrank
         volatile unsigned* mine = reinterpret_cast<volatile unsigned*>(flags) + slot * NSB_MAX_PEERS + r;
         unsigned spin = 0;
         while ((int)(*mine - epoch) < 0) {
-            if (++spin > (1u << 25)) __trap();
+            if (++spin > max_spins) __trap();   // a lost peer must not hang the GPU (bound: nsb200_create, NSB200_BARRIER_SPINS)
         }
         __threadfence_system();
     }
@@ -282,6 +282,8 @@ NSB_HD double nsb_hou_li(int kx, int ky, int kz, int N) {
 }
 
 // solver.c:697-718 then :1732-1737 (dealias == 1) or :1744-1751 (dealias == 2) for one mode; kmax2 carries N when dealias == 2
+// (HOULI is a template parameter so that exp / pow stay out of the register budget of the 2/3-rule kernel)
+template <bool HOULI = false>
 NSB_HD void project_mode(int kx, int ky, int kz, double norm, int dealias, int kmax2, cplx& c0, cplx& c1, cplx& c2) {
     c0 = rmul(norm, c0); c1 = rmul(norm, c1); c2 = rmul(norm, c2);
     const int k2 = kx * kx + ky * ky + kz * kz;
@@ -295,12 +297,15 @@ NSB_HD void project_mode(int kx, int ky, int kz, double norm, int dealias, int k
         c0 = c1 = c2 = mk(0.0, 0.0);
     }
     if (dealias == 1 && k2 > kmax2) c0 = c1 = c2 = mk(0.0, 0.0);
-    if (dealias == 2) {
-        const double f = nsb_hou_li(kx, ky, kz, kmax2);
-        c0 = rmul(f, c0); c1 = rmul(f, c1); c2 = rmul(f, c2);
+    if constexpr (HOULI) {
+        if (dealias == 2) {
+            const double f = nsb_hou_li(kx, ky, kz, kmax2);
+            c0 = rmul(f, c0); c1 = rmul(f, c1); c2 = rmul(f, c2);
+        }
     }
 }
 
+template <bool HOULI>
 __global__ void k_rk_stage(const RkArgs a) {
     const Geom g = a.g;
     // skip_outside: walk the window rows only; otherwise every row (modes outside the window then see c = 0)
@@ -329,7 +334,7 @@ __global__ void k_rk_stage(const RkArgs a) {
             for (int d = 0; d < 3; ++d) u0[d] = (a.stage != 4) ? NSB_LDCG(a.u[d] + e) : mk(0.0, 0.0);
 #pragma unroll
             for (int d = 0; d < 3; ++d) ac[d] = (a.stage >= 1 && a.stage <= 3) ? NSB_LDCG(a.acc[d] + e) : mk(0.0, 0.0);
-            project_mode(kx, ky, k, a.norm, a.dealias, a.kmax2, c[0], c[1], c[2]);
+            project_mode<HOULI>(kx, ky, k, a.norm, a.dealias, a.kmax2, c[0], c[1], c[2]);
             if (a.stage == 4) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) a.acc[d][e] = c[d];

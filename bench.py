@@ -271,6 +271,47 @@ def fft_sweep(nsb, capi, local, sizes=(128, 256, 512, 1024)):
                     "cuFFT = cufftPlanMany D2Z/Z2D batch 3 through ctypes", "hbm_peak_gbs": peak, "rows": rows}
 
 
+def fft_sweep_multi(nsb, capi, local, rank, world, fresh_uid, max_over_ranks, sizes=(512, 1024)):
+    """The same pair on `world` GPUs: the transposed transforms the solver uses (one slab exchange per transform, fused into
+    the store phase of the y-inverse / x-forward pass over NVLink).  All ranks call this."""
+    import torch
+    peak, _ = peaks()
+    rows = []
+    for n in sizes:
+        S = scalar_bytes(n)
+        free, _tot = torch.cuda.mem_get_info()
+        row = {"N": n, "n_gpus": world, "bytes_per_c2r_r2c_pair_of_3": 36.0 * S}
+        need = 21.5 * S / world * 1.02 + (1 << 30)
+        ok = torch.tensor([1 if free >= need else 0], device="cuda")
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            row["unavailable"] = "needs %.0f GB per GPU" % (21.5 * S / world / 1e9)
+            rows.append(row)
+            continue
+        iters = 10 if n <= 512 else 3
+        s = nsb.Solver(n, nu=1e-3, device=local, rank=rank, n_ranks=world, nccl_unique_id=fresh_uid())
+        s.initial_conditions("RANDOM_PHASE", seed=1, kp=4.0)
+        s.time_op(capi.OP_FFT_C2R_R2C, 2)
+        torch.cuda.synchronize(); torch.distributed.barrier()
+        ms = max_over_ranks(s.time_op(capi.OP_FFT_C2R_R2C, iters)) / iters
+        l0 = s.link_bytes()
+        s.profile(True)
+        s.time_op(capi.OP_FFT_C2R_R2C, 2)
+        pr = s.profile_read()
+        s.profile(False)
+        link = (s.link_bytes() - l0) / 2
+        link_ms = sum(pr[k][0] for k in ("y_inv", "x_fwd") if k in pr) / 2
+        s.close()
+        row.update({"ours_ms": ms, "ours_gbs_aggregate": 36.0 * S / ms / 1e6, "ours_frac_of_hbm_peak_per_gpu": 36.0 * S / world / ms / 1e6 / peak,
+                    "a2a_bytes_per_gpu": link, "a2a_store_phase_ms": link_ms,
+                    "a2a_gbs_per_gpu": link / (link_ms * 1e-3) / 1e9 if link_ms > 0 else None,
+                    "a2a_frac_of_900": link / (link_ms * 1e-3) / 1e9 / 900.0 if link_ms > 0 else None})
+        rows.append(row)
+    return {"what": "batched (3 fields) transposed c2r + r2c pair on %d GPUs, full spectrum, FP64, max over ranks; a2a = bytes each GPU "
+                    "stores into its peers / time of the two store-phase kernels (which also read HBM and transform)" % world,
+            "rows": rows}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 
 def load_digest(n):
@@ -565,11 +606,19 @@ def ours(args):
             s2.close()
         except Exception as ex:
             secondary = {"unavailable": repr(ex)[:300]}
+    sweep_multi = None
+    if args.sweep and world > 1:
+        try:
+            sweep_multi = fft_sweep_multi(nsb, capi, local, rank, world, fresh_uid, max_over_ranks)
+        except Exception as ex:
+            sweep_multi = {"unavailable": repr(ex)[:300]}
     if world > 1:
         dist.barrier()
     if rank == 0:
         if secondary is not None:
             out["secondary"] = secondary
+        if sweep_multi is not None:
+            out["fft_sweep"] = sweep_multi
         if args.sweep and world == 1:
             try:
                 out["fft_sweep"] = fft_sweep(nsb, capi, local)

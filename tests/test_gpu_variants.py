@@ -67,6 +67,17 @@ def test_strided_and_fused_z_kernel_generations_agree_to_rounding():
         assert abs(e - e0) <= 1e-13 * abs(e0)
 
 
+def test_1024_general_warp_kernels_agree_with_the_first_generation():
+    """1024^3: z kernels in the general warp-per-transform form (two mirrored pairs per lane, radix-16 middle pass, twiddle
+    powers formed on the fly) against the first-generation kernels (4-pass plan, table twiddles): two steps, energy to 1e-13.
+    (The 1-D transforms themselves are checked against a long double DFT in tests/host_emul.)"""
+    _, e0 = run_variant(1024, {})
+    _, e1 = run_variant(1024, {"NSB200_ZF": "old"})
+    _, e2 = run_variant(1024, {"NSB200_ZF": "warp"})          # the general fused kernel too (not the default at 1024)
+    assert abs(e2 - e0) <= 1e-13 * abs(e0)
+    assert abs(e1 - e0) <= 1e-13 * abs(e0)
+
+
 def test_two_ranks_match_one_rank():
     import torch
     if torch.cuda.device_count() < 2:
