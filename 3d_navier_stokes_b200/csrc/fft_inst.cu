@@ -111,6 +111,10 @@ int pipe_setup() {
     e = cudaFuncSetAttribute(k_fft_strided_ring<BP, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RingCfg<BP>::SMEM);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fft_strided_ring<BP, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RingCfg<BP>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fft_strided_ring<BP, FWD, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RingCfg<BP, 1, 2>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fft_strided_ring<BP, INV, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RingCfg<BP, 1, 2>::SMEM);
     return (int)e;
 }
 int pipe_occupancy() {
@@ -139,16 +143,33 @@ int strided_ring(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer
     else k_fft_strided_ring<BP, INV><<<grid, RingCfg<BP>::THREADS, RingCfg<BP>::SMEM, s>>>(*a, *maps, pa);
     return (int)cudaGetLastError();
 }
+// light ring pass (one group, two buffers) on a restricted, persistent grid: the link-bound store phases of the overlapped schedule
+int strided_link(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s) {
+    typedef RingCfg<BP, 1, 2> LC;
+    PipeArgs pa;
+    pa.nzt = (a->nzv + PT - 1) / PT;
+    pa.n_outer_eff = n_outer_eff;
+    pa.total_tiles = pa.nzt * n_outer_eff * nfields;
+    if (pa.total_tiles == 0) return 0;
+    int grid = pa.total_tiles < max_ctas ? pa.total_tiles : max_ctas;
+    pa.tiles_per_cta = (pa.total_tiles + grid - 1) / grid;
+    grid = (pa.total_tiles + pa.tiles_per_cta - 1) / pa.tiles_per_cta;
+    if (dir == FWD) k_fft_strided_ring<BP, FWD, 1, 2><<<grid, LC::THREADS, LC::SMEM, s>>>(*a, *maps, pa);
+    else k_fft_strided_ring<BP, INV, 1, 2><<<grid, LC::THREADS, LC::SMEM, s>>>(*a, *maps, pa);
+    return (int)cudaGetLastError();
+}
 #define NSB_PIPE_FN strided_pipe
 #define NSB_PIPE_TCOLS PT
 #define NSB_PIPE_OCC pipe_occupancy
 #define NSB_RING_FN strided_ring
+#define NSB_LINK_FN strided_link
 #else
 int pipe_setup() { return 0; }
 #define NSB_PIPE_FN nullptr
 #define NSB_PIPE_TCOLS 0
 #define NSB_PIPE_OCC nullptr
 #define NSB_RING_FN nullptr
+#define NSB_LINK_FN nullptr
 #endif
 
 int zlaunch(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s) {
@@ -193,4 +214,4 @@ int zocc(int which) {
 extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, NSB_PIPE_TCOLS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G,
      // 1024: the general fused kernel (249 registers, 2 x 3 warps per SM) measured slower than the first generation (117.5 vs 108.8 ms
      // per step), the stand-alone passes faster (65 vs 56 % of the HBM peak): NSB200_ZF=warp still selects it for experiments
-     NSB_HAVE_ZFW ? 1 : (NSB_HAVE_ZG ? -1 : 0), (NSB_HAVE_ZFW || NSB_HAVE_ZG) ? 4 : 0, (NSB_HAVE_ZFW || NSB_HAVE_ZG) ? 4 : 0}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC, NSB_RING_FN};
+     NSB_HAVE_ZFW ? 1 : (NSB_HAVE_ZG ? -1 : 0), (NSB_HAVE_ZFW || NSB_HAVE_ZG) ? 4 : 0, (NSB_HAVE_ZFW || NSB_HAVE_ZG) ? 4 : 0}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC, NSB_RING_FN, NSB_LINK_FN};

@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
 // forward in the buffer of u_{t+1}.
 template <class P> struct ZWarpCfg {
     static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && P::M1 == 64, "warp-per-transform kernel: plan 8 x R2 x 8 with 64 butterflies per pass");
-    static_assert(P::NB2 % 32 == 0 && 32 % P::M2 == 0, "pass 2 must split evenly over the warp with one twiddle set per lane");
+    static_assert(P::NB2 % 32 == 0 && 32 % P::M2 == 0 && P::R2 == 8, "pass 2 must split evenly over the warp with one twiddle set per lane");
     static constexpr int THREADS = 96;
     static constexpr int SMEM = 6 * P::NPAD * 16;
 #ifndef NSB_ZFW_MINB
@@ -752,12 +752,14 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
     int bA, bB; bool self;
     zw_lane_pair<P>(L, bA, bB, self);
     const int rbA = fft_row_base<P>(bA), rbB = fft_row_base<P>(bB);
-    cplx w1[7], w2[P::R2 - 1];
+    cplx w1[7];
     zw_load_tw1<P>(L, tw, w1);
-    load_tw_pass2<P>(L, tw, w2);
+    // pass-2 twiddles W^{8 (L % 8) kp}: powers 1, 2, 4 in registers, the others formed on the fly (the kernel is bound by the
+    // shared-memory pipe, not by FP64, and the 16 registers saved end the spilling at 4 CTAs per SM)
+    const cplx w2a = tw[P::R1 * (L % P::M2)], w2b = tw[P::R1 * (L % P::M2) * 2], w2c = tw[P::R1 * (L % P::M2) * 4];
     for (long long pr = blockIdx.x; pr < a.npairs; pr += gridDim.x) {
         const long long roff = 2 * pr * a.rs;
-#if defined(__CUDA_ARCH__) && defined(NSB_ZFW_PREFETCH)
+#if defined(__CUDA_ARCH__) && !defined(NSB_ZFW_NO_PREFETCH)
         // pull the next pair of this CTA into L2 while this one is transformed (12 rows of kz_in entries)
         if (pr + gridDim.x < a.npairs) {
             const long long nroff = 2 * (pr + gridDim.x) * a.rs;
@@ -782,7 +784,7 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
             });
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_rw<P, INV, 1>(L + 32 * i, buf, w2);
+            for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r8_base<P, INV, 1>(L + 32 * i, buf, w2a, w2b, w2c);
             __syncwarp();
             zw_last_pair<P, INV>(L, buf, ca, cb);
 #pragma unroll
@@ -805,7 +807,7 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
         zw_scatter_pair<P>(bA, bB, buf, ca, cb);
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_rw<P, FWD, 1>(L + 32 * i, buf, w2);
+        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r8_base<P, FWD, 1>(L + 32 * i, buf, w2a, w2b, w2c);
         __syncwarp();
         zw_last_pair<P, FWD>(L, buf, ca, cb);
         cplx* oa = a.base + t * a.fstride + roff;
@@ -832,9 +834,9 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const Z
     const int kzin = a.kz_in;
     int bA, bB; bool self;
     zw_lane_pair<P>(L, bA, bB, self);
-    cplx w1[7], w2[P::R2 - 1];
+    cplx w1[7];
     zw_load_tw1<P>(L, tw, w1);
-    load_tw_pass2<P>(L, tw, w2);
+    const cplx w2a = tw[P::R1 * (L % P::M2)], w2b = tw[P::R1 * (L % P::M2) * 2], w2c = tw[P::R1 * (L % P::M2) * 4];   // see k_z_fused_w
     for (long long pr = (long long)blockIdx.x * WARPS + wp; pr < a.npairs; pr += (long long)gridDim.x * WARPS) {
         cplx* ra = F + 2 * pr * a.rs;
         cplx* rb = ra + a.rs;
@@ -844,7 +846,7 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const Z
         });
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_rw<P, INV, 1>(L + 32 * i, buf, w2);
+        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r8_base<P, INV, 1>(L + 32 * i, buf, w2a, w2b, w2c);
         __syncwarp();
         cplx va[8], vb[8];
         zw_last_pair<P, INV>(L, buf, va, vb);
@@ -871,9 +873,9 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const Z
     const int kzout = a.kz_out;
     int bA, bB; bool self;
     zw_lane_pair<P>(L, bA, bB, self);
-    cplx w1[7], w2[P::R2 - 1];
+    cplx w1[7];
     zw_load_tw1<P>(L, tw, w1);
-    load_tw_pass2<P>(L, tw, w2);
+    const cplx w2a = tw[P::R1 * (L % P::M2)], w2b = tw[P::R1 * (L % P::M2) * 2], w2c = tw[P::R1 * (L % P::M2) * 4];   // see k_z_fused_w
     for (long long pr = (long long)blockIdx.x * WARPS + wp; pr < a.npairs; pr += (long long)gridDim.x * WARPS) {
         cplx* ra = F + 2 * pr * a.rs;
         cplx* rb = ra + a.rs;
@@ -889,7 +891,7 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const Z
         zw_scatter_pair<P>(bA, bB, buf, ca, cb);
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_rw<P, FWD, 1>(L + 32 * i, buf, w2);
+        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r8_base<P, FWD, 1>(L + 32 * i, buf, w2a, w2b, w2c);
         __syncwarp();
         zw_last_pair<P, FWD>(L, buf, ca, cb);
         __syncwarp();                                    // in place: every lane has read the real rows before the spectra overwrite them
@@ -1187,10 +1189,12 @@ __global__ void __launch_bounds__(ZGenCfg<P>::PASS_THREADS, 3) k_zg_r2c(const ZA
 // single-group pipeline ran its 16 warps in lock step: 7 k cycles per tile against 6 k of HBM time).  Every thread
 // owns the Hermitian-mirrored butterfly pair (q, 64 - q) of pass 1, so one set of twiddle registers serves both
 // (see zw_bfly_pair), and the pass-2 butterflies q, q + 32 share theirs: no twiddle loads inside the tile loop.
-template <class P> struct RingCfg {
+template <class P, int NGROUP_ = 2, int NBUF_ = 3> struct RingCfg {
     static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && P::M1 == 64 && P::NB2 == 64 && P::ROW == P::M1,
                   "ring kernel: unpadded 8 x 8 x 8 plan");
-    static constexpr int T = 8, GROUP = 256, NGROUP = 2, NBUF = 3;
+    // NGROUP = 1, NBUF = 2 is the light variant for link-bound store phases of the overlapped multi-GPU schedule: 256
+    // threads, 128 KB, at most 128 registers, so that a kernel of the other stream still fits on the same SM
+    static constexpr int T = 8, GROUP = 256, NGROUP = NGROUP_, NBUF = NBUF_;
     static constexpr int THREADS = NGROUP * GROUP;
     static constexpr size_t SMEM = (size_t)NBUF * P::N * T * sizeof(cplx);
 #ifndef NSB_RING_SHIFT
@@ -1198,9 +1202,10 @@ template <class P> struct RingCfg {
 #endif
     static constexpr int SHIFT = NSB_RING_SHIFT;      // slots group 1 runs behind group 0
 };
-template <class P, int DIR>
-__global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring(const StridedArgs a, const __grid_constant__ TmaMaps maps, const PipeArgs pa) {
-    constexpr int T = RingCfg<P>::T, N = P::N, NBUF = RingCfg<P>::NBUF, GROUP = RingCfg<P>::GROUP, SHIFT = RingCfg<P>::SHIFT;
+template <class P, int DIR, int NGROUP = 2, int NBUF_ = 3>
+__global__ void __launch_bounds__(RingCfg<P, NGROUP, NBUF_>::THREADS, 3 - NGROUP) k_fft_strided_ring(const StridedArgs a, const __grid_constant__ TmaMaps maps, const PipeArgs pa) {
+    typedef RingCfg<P, NGROUP, NBUF_> Cfg;
+    constexpr int T = Cfg::T, N = P::N, NBUF = Cfg::NBUF, GROUP = Cfg::GROUP, SHIFT = Cfg::SHIFT;
     extern __shared__ __align__(1024) unsigned char nsb_smem_raw[];
     cplx* smem = reinterpret_cast<cplx*>(nsb_smem_raw);
     __shared__ __align__(8) unsigned long long s_bar[NBUF];
@@ -1250,8 +1255,8 @@ __global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring(con
     const int p2p = a.out_p2p, rank_lo = a.out_rank_lo;
     // Time is cut into slots separated by CTA barriers; a group spends three consecutive slots on a tile (pass 1, pass 2,
     // last pass + stores) and group 1 runs SHIFT slots behind group 0, so the two groups are always in different passes.
-    const int ntg = (nt - g + 1) / 2;                  // tiles of this group: it = g, g + 2, ...
-    const int nslots = 3 * ((nt + 1) / 2) + SHIFT;
+    const int ntg = (nt - g + NGROUP - 1) / NGROUP;    // tiles of this group: it = g, g + NGROUP, ...
+    const int nslots = 3 * ((nt + NGROUP - 1) / NGROUP) + (NGROUP - 1) * SHIFT;
     int buf = 0;
     bool valid = false;
     cplx* dst = nullptr;
@@ -1260,7 +1265,7 @@ __global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring(con
         const int ls = s - g * SHIFT;
         const bool active = ls >= 0 && ls < 3 * ntg;
         const int ph = active ? ls % 3 : -1;
-        const int it = g + 2 * (ls / 3);
+        const int it = g + NGROUP * (ls / 3);
         if (ph == 0) {
             const int t = t0 + it;
             buf = it % NBUF;

@@ -24,6 +24,8 @@ struct FftOps {
     int (*pipe_occupancy)(void);
     // persistent two-group ring pass (one CTA per SM, T = 8, TMA, natural input layout); NULL when not built for this N
     int (*strided_ring)(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s);
+    // light variant of it (one group, two buffers, 256 threads) on a restricted persistent grid: link-bound store phases
+    int (*strided_link)(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s);
 };
 
 const FftOps* nsb_get_fft_ops(int N);

@@ -148,6 +148,7 @@ struct nsb200_ctx {
     bool prune = true;             // use the dealias support windows (NSB200_NO_PRUNE=1 disables)
     bool use_tma = true;           // TMA tile loads in the strided passes (NSB200_NO_TMA=1: cp.async path)
     bool use_pipe = false;         // persistent double-buffered strided pass where built (NSB200_PIPE=1)
+    bool link_light = false;       // link-bound store phases as the light ring pass beside one-shot partner passes (NSB200_LINK_LIGHT=1)
     bool use_ring = true;          // persistent two-group ring pass where built (default; NSB200_RING=0 disables)
     int pipe_ctas = 0;
     int link_ctas = 64;            // CTAs (= SMs) given to a link-bound store phase in the overlapped schedule (NSB200_LINK_CTAS)
@@ -345,8 +346,12 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
     // the persistent kernel also serves the overlapped multi-GPU schedule: a link-bound store phase runs on a
     // restricted grid (link_ctas SMs) so that the other stream's HBM-bound pass gets the rest of the GPU
     const bool link_limited = ps.p2p_out && h->overlap && h->link_ctas > 0;
-    const bool ring = h->use_ring && !link_limited && !ps.copy_only && h->use_tma && natural_in && h->ops->strided_ring != nullptr;
-    const bool pipe = ring || ((h->use_pipe || link_limited) && h->use_tma && natural_in && h->ops->strided_pipe != nullptr);
+    // link-bound store phases of the two-stream schedule: the light ring pass (256 threads, 128 KB) on link_ctas SMs, so that
+    // the other stream's pass fits beside it; that other pass then has to be the one-shot kernel (64 KB), not the full ring (192 KB)
+    const bool light = link_limited && h->link_light && h->use_tma && natural_in && h->ops->strided_link != nullptr;
+    const bool partner = h->p2p && h->overlap && h->link_light && !ps.p2p_out;
+    const bool ring = h->use_ring && !link_limited && !partner && !ps.copy_only && h->use_tma && natural_in && h->ops->strided_ring != nullptr;
+    const bool pipe = ring || light || ((h->use_pipe || link_limited) && h->use_tma && natural_in && h->ops->strided_pipe != nullptr);
     if (h->use_tma && natural_in && (h->ops->strided_T == 8 || pipe)) {
         memset(&maps, 0, sizeof maps);
         const int bc = pipe ? h->ops->pipe_T : 8;
@@ -365,7 +370,8 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
         const double bytes = 16.0 * field_cnt * (double)n_outer * ps.nzv * (in_cnt + out_cnt);
         if (ps.p2p_out) h->link_bytes += 16.0 * field_cnt * (double)n_outer * ps.nzv * out_cnt * (h->nranks - 1) / h->nranks;
         ProfScope psc(h, ps.axis == 'y' ? (ps.dir == INV ? NSB200_PC_Y_INV : NSB200_PC_Y_FWD) : (ps.dir == INV ? NSB200_PC_X_INV : NSB200_PC_X_FWD), bytes, st);
-        if (ring) CKI(h->ops->strided_ring(ps.dir, &a, mp, n_outer, field_cnt, h->sm_count, st));
+        if (light) CKI(h->ops->strided_link(ps.dir, &a, mp, n_outer, field_cnt, h->link_ctas, st));
+        else if (ring) CKI(h->ops->strided_ring(ps.dir, &a, mp, n_outer, field_cnt, h->sm_count, st));
         else if (pipe) CKI(h->ops->strided_pipe(ps.dir, &a, mp, n_outer, field_cnt, link_limited ? h->link_ctas : h->pipe_ctas, st));
         else CKI(h->ops->strided(ps.dir, &a, mp, n_outer, field_cnt, st));
     }
@@ -754,6 +760,7 @@ int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, doub
     { const char* e = getenv("NSB200_NO_FUSE_CURL"); h->fuse_curl = !(e && e[0] == '1'); }
     { const char* e = getenv("NSB200_BARRIER_SPINS"); if (e && atof(e) >= 1024.0) h->barrier_spins = (unsigned)std::min(atof(e), 4.0e9); }
     { const char* e = getenv("NSB200_PIPE"); h->use_pipe = (e && e[0] == '1'); }
+    { const char* e = getenv("NSB200_LINK_LIGHT"); h->link_light = (e && e[0] == '1'); }
     { const char* e = getenv("NSB200_RING"); h->use_ring = !(e && e[0] == '0') && !h->use_pipe; }
     h->link_ctas = (h->nranks >= 8) ? 128 : 96;   // measured: 4 ranks 11.22 -> 10.58 ms (96), 8 ranks 6.26 -> 6.02 ms (128)
     { const char* e = getenv("NSB200_LINK_CTAS"); if (e) h->link_ctas = atoi(e); }

@@ -54,9 +54,14 @@ int nsb200_device_count(void);
  *   dealias_mode    NSB200_DEALIAS_*
  *   rank, n_ranks   slab decomposition over kx exactly like fftw_mpi_local_size_many with
  *                   FFTW_MPI_DEFAULT_BLOCK (solver.c:1845): local_Nx = Nx / n_ranks planes starting at
- *                   rank * local_Nx.  n_ranks must divide Nx.
- *   nccl_unique_id  128-byte ncclUniqueId shared by all ranks (NULL when n_ranks == 1).  The slab
- *                   exchange inside each 3-D transform is an NCCL all-to-all.                       */
+ *                   rank * local_Nx.  n_ranks must divide Nx and Nx / n_ranks must be even.
+ *   nccl_unique_id  128-byte ncclUniqueId shared by all ranks (NULL when n_ranks == 1).
+ * Several ranks: the slab exchange inside each 3-D transform is fused into the store phase of the FFT kernels, which
+ * write straight into the peers' buffers over NVLink (CUDA IPC mapping of every rank's allocation, flag barriers over
+ * peer memory).  That needs all ranks on one node with peer access, n_ranks <= 8, and lock-step calls; NCCL then only
+ * carries the set-up all-gathers and the diagnostics all-reduce.  NSB200_NO_P2P=1 (or missing peer access) selects the
+ * fallback, grouped ncclSend / ncclRecv on a second stream.  The multi-rank 3-D transform API, the real-space dumps and
+ * the TAYLOR_GREEN / SHAPIRO initial conditions need the peer-memory path.                                              */
 int nsb200_create(nsb200_ctx** out, const long N[3], int device, double nu, double visc_pow, int system,
                   int dealias_mode, int rank, int n_ranks, const void* nccl_unique_id);
 /* Replaces FreeMemory (solver.c:2078-2157). */
@@ -131,7 +136,8 @@ int nsb200_spectra(nsb200_ctx* h, double* enrg_spect, double* enst_spect, int n_
 
 /* Replaces the non-transposed batch plans fftw_3d_dft_batch_r2c / _c2r (solver.c:2056-2057) as used by
  * InitialConditions (solver.c:1573,1599) and the real-space dumps (hdf5_funcs.c:588,665): three
- * interleaved components, unnormalised, host arrays in the reference layouts.  Single rank only. */
+ * interleaved components, unnormalised, host arrays in the reference layouts: this rank's x slab
+ * [local_Nx][Ny][Nz+2][3] on the real side, its kx slab [local_Nx][Ny][Nz/2+1][3] on the Fourier side. */
 int nsb200_fft_r2c(nsb200_ctx* h, const double* real_in, double* cplx_out);
 int nsb200_fft_c2r(nsb200_ctx* h, const double* cplx_in, double* real_out);
 
@@ -139,12 +145,12 @@ int nsb200_fft_c2r(nsb200_ctx* h, const double* cplx_in, double* real_out);
  * zero-filled and written by the reference, hdf5_funcs.c:186,639, but never computed - SURVEY Q13), and the
  * real-space fields u (which = 0) / w (which = 1) as WriteDataToFile produces them under __REALSPACE /
  * __VORT_REAL: non-transposed batch c2r and 1/(NxNyNz) scaling (hdf5_funcs.c:588-602, 665-679), layout
- * [Nx][Ny][Nz+2][3].  nsb200_download_real is single rank only. */
+ * [local_Nx][Ny][Nz+2][3] (this rank's x slab). */
 int nsb200_download_what(nsb200_ctx* h, double* w_hat_host);
 int nsb200_download_real(nsb200_ctx* h, int which, double* real_host);
 
 /* Replaces InitialConditions (solver.c:1537-1648, fixes F3/F5) on the device: "TAYLOR_GREEN",
- * "SHAPIRO" (real-space fill, batch r2c, dealias) or "RANDOM_PHASE" (the partition-independent
+ * "SHAPIRO" (real-space fill, batch r2c, dealias; any number of ranks) or "RANDOM_PHASE" (the partition-independent
  * synthetic field of SURVEY 8d: seed, peak wavenumber kp, rescaled to `energy`). */
 int nsb200_initial_condition(nsb200_ctx* h, const char* name, unsigned long long seed, double kp, double energy);
 
