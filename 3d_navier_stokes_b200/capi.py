@@ -19,6 +19,8 @@ SYMBOLS = [
     ("nsb200_destroy", ctypes.c_int, [ctypes.c_void_p]),
     ("nsb200_get_nccl_unique_id", ctypes.c_int, [ctypes.c_void_p]),
     ("nsb200_exchange_layout", ctypes.c_int, [ctypes.c_long, ctypes.c_int, ctypes.c_long, _LP]),
+    ("nsb200_peer_store_layout", ctypes.c_int, [ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int,
+                                                ctypes.POINTER(ctypes.c_longlong)]),
     ("nsb200_plane_owner", ctypes.c_int, [ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.POINTER(ctypes.c_int), _LP]),
     ("nsb200_local_slab", ctypes.c_int, [ctypes.c_void_p, _LP, _LP]),
     ("nsb200_local_fourier_elems", ctypes.c_long, [ctypes.c_void_p]),

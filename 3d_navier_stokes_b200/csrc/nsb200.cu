@@ -257,6 +257,26 @@ static void exchange_layout(long N, int n_ranks, long rs, long out[5]) {
     out[0] = sh; out[1] = ny_loc - 1; out[2] = nx_loc * ny_loc * rs; out[3] = ny_loc * rs; out[4] = rs;
 }
 
+// Where the fused exchange puts a sender's rows inside the RECEIVER's field (pure host logic, exported as
+// nsb200_peer_store_layout so the CPU tests drive the same arithmetic as run_pass).  The receivers see natural layouts:
+//   dir 0 (inverse, y pass sends):  element (li, y, kz) of the sender -> rank y / ny_loc, buffer [kx][y_loc][rs] with
+//          kx = li * P + rank (cyclic planes) or rank * nx_loc + li (contiguous slabs), at  out[0] + li * out[1] + (y % ny_loc) * rs + kz
+//   dir 1 (forward, x pass sends):  element (y_loc, kx, kz) -> the owner of plane kx, Fourier slab [kx_loc][y][rs], at
+//          out[0] + y_loc * out[1] + local_index(kx) * out[2] + kz
+static void peer_store_layout(long N, int n_ranks, int rank, int cyclic, long rs, int dir, long long out[3]) {
+    const long long ny_loc = N / n_ranks, nx_loc = N / n_ranks;
+    if (dir == 0) {
+        const long long row = ny_loc * rs;                      // one kx row of the receiver
+        out[0] = cyclic ? row * rank : row * rank * nx_loc;
+        out[1] = cyclic ? row * n_ranks : row;
+        out[2] = rs;
+    } else {
+        out[0] = (long long)rank * ny_loc * rs;
+        out[1] = rs;
+        out[2] = (long long)N * rs;                             // plane stride of the receiver's slab
+    }
+}
+
 // One strided c2c pass.  axis 'y': Fourier slab [kx_loc][ky][kz], outer = kx_loc.  axis 'x': after the slab
 // exchange [kx][y_loc][kz], outer = y_loc.  `exch` selects the all-to-all block layout on the output
 // ('o', inverse y pass) or input ('i', forward y pass) side: element n of the transformed axis lives
@@ -307,10 +327,10 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
                     // NATURAL kx order (kx = li*P + rank with the cyclic distribution, rank*nx_loc + li with contiguous
                     // slabs), so the receiving x pass reads an ordinary field (TMA tiles, persistent ring pass).
                     a.out_p2p = 1; a.out_s1 = 0;
-                    const long long row = (long long)h->ny_loc * ps.out_rs;          // one kx row of the receiver
-                    a.out_so = h->cyclic ? row * h->nranks : row;
-                    const long long first = h->cyclic ? row * h->rank : row * h->rank * h->nx_loc;
-                    for (int f = 0; f < field_cnt; ++f) a.dst[f] += first;
+                    long long PL[3];
+                    peer_store_layout(N, h->nranks, h->rank, h->cyclic ? 1 : 0, ps.out_rs, 0, PL);
+                    a.out_so = PL[1];
+                    for (int f = 0; f < field_cnt; ++f) a.dst[f] += PL[0];
                     for (int r = 0; r < h->nranks; ++r) a.peer_delta[r] = h->peer_delta[r];
                 }
             } else {
@@ -333,8 +353,10 @@ static int run_pass(nsb200_ctx* h, const PassSpec& ps, cplx* const* src, cplx* c
             a.out_p2p = 1; a.out_s1 = 0;
             if (h->cyclic) { a.out_rank_lo = 1; a.out_shift = lp; a.out_mask = h->nranks - 1; }
             else { a.out_shift = (int)L[0]; a.out_mask = (int)L[1]; }
-            a.out_s2 = (long long)N * ps.out_rs;                               // plane stride of the receiver's slab
-            for (int f = 0; f < field_cnt; ++f) a.dst[f] += (long long)h->rank * h->ny_loc * ps.out_rs;
+            long long PL[3];
+            peer_store_layout(N, h->nranks, h->rank, h->cyclic ? 1 : 0, ps.out_rs, 1, PL);
+            a.out_s2 = PL[2];
+            for (int f = 0; f < field_cnt; ++f) a.dst[f] += PL[0];
             for (int r = 0; r < h->nranks; ++r) a.peer_delta[r] = h->peer_delta[r];
         }
     }
@@ -686,6 +708,13 @@ const char* nsb200_last_error(void) { return g_err.c_str(); }
 int nsb200_exchange_layout(long N, int n_ranks, long row_stride, long out[5]) {
     if (!out || n_ranks < 1 || N < 1 || N % n_ranks != 0) return fail("nsb200_exchange_layout: bad argument");
     exchange_layout(N, n_ranks, row_stride, out);
+    return 0;
+}
+
+int nsb200_peer_store_layout(long N, int n_ranks, int rank, int cyclic, long row_stride, int direction, long long out[3]) {
+    if (!out || n_ranks < 1 || N < 1 || N % n_ranks != 0 || rank < 0 || rank >= n_ranks || (direction != 0 && direction != 1))
+        return fail("nsb200_peer_store_layout: bad argument");
+    peer_store_layout(N, n_ranks, rank, cyclic, row_stride, direction, out);
     return 0;
 }
 

@@ -77,6 +77,15 @@ int nsb200_get_nccl_unique_id(void* out128);
  * fftw_mpi_execute_dft_* (solver.c:656-683). */
 int nsb200_exchange_layout(long N, int n_ranks, long row_stride, long out[5]);
 
+/* Addressing of the fused exchange (pure host logic): where a sender's rows land inside the RECEIVER's field, which is in
+ * natural order so that the receiving pass is an ordinary one.
+ *   direction 0 (inverse side, the y pass sends): element (li, y, kz) of rank `rank` goes to rank y / (N/P), into its
+ *     [kx][y_loc][row_stride] buffer at  out[0] + li * out[1] + (y % (N/P)) * row_stride + kz
+ *     (kx = li * P + rank with cyclic planes, rank * N/P + li with contiguous slabs);
+ *   direction 1 (forward side, the x pass sends): element (y_loc, kx, kz) goes to the owner of plane kx
+ *     (nsb200_plane_owner), into its Fourier slab [kx_loc][y][row_stride] at  out[0] + y_loc * out[1] + local_index * out[2] + kz. */
+int nsb200_peer_store_layout(long N, int n_ranks, int rank, int cyclic, long row_stride, int direction, long long out[3]);
+
 /* Device-side ownership of Fourier plane kx_index.  The boundary keeps the reference's contiguous slabs
  * (rank = kx / (N/P)); inside the library the planes are dealt out cyclically (rank = kx % P, local index
  * kx / P) when the peer mapping is available, so that every rank owns an equal share of the dealiased support
