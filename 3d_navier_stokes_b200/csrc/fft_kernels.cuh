@@ -4,10 +4,15 @@
 //   k_fft_strided   c2c pass along x or y: a CTA owns a tile of T consecutive kz columns
 //                   x N points, so every global access is T*16 contiguous bytes; tile-interleaved
 //                   shared memory ([element][T]) makes all exchanges conflict free.
+//   k_fft_strided_ring  the persistent form of that pass (N = 512): one CTA per SM, a TMA-fed ring of three tiles, two
+//                   slot-shifted groups of 256 threads; k_fft_strided_pipe: its single-group predecessor, still used on a
+//                   restricted grid for the link-bound store phases of the overlapped multi-GPU schedule.
 //   k_z_c2r/k_z_r2c contiguous z pencils, two real pencils packed in one complex transform.
 //   k_z_fused       z c2r of (u, w) -> u x w -> z r2c in one kernel: the six real-space fields of a
 //                   pencil pair never leave the SM (reference loops solver.c:664-677 between the
 //                   transforms of :656/:658 and :683).
+//   k_z_fused_w, k_z_c2r_w, k_z_r2c_w (N = 512), k_zg_* (general form, N = 1024)  the same z kernels with ONE WARP per
+//                   transform and Hermitian-mirrored butterfly pairs per lane (second generation).
 #pragma once
 #include <cuda.h>
 #include "fft_core.cuh"
