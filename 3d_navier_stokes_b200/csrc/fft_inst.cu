@@ -1,4 +1,7 @@
 // Instantiates the FFT kernels for one grid size: compile with -DNSB_N=<16|32|...|1024>.
+#include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdlib>
 #include "fft_ops.h"
 
@@ -91,7 +94,7 @@ int strided(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff,
 constexpr int PT = NSB_PIPE_T;
 constexpr size_t kPipeSmem = (size_t)2 * NSB_N * PT * sizeof(cplx);
 int strided_pipe(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s) {
-    PipeArgs pa;
+    PipeArgs pa = {};
     pa.nzt = (a->nzv + PT - 1) / PT;
     pa.n_outer_eff = n_outer_eff;
     pa.total_tiles = pa.nzt * n_outer_eff * nfields;
@@ -112,6 +115,10 @@ int pipe_setup() {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fft_strided_ring<BP, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RingCfg<BP>::SMEM);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fft_strided_ring_fr<BP, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RingCfg<BP>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fft_strided_ring_fr<BP, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RingCfg<BP>::SMEM);
+    if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fft_strided_ring<BP, FWD, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RingCfg<BP, 1, 2>::SMEM);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_fft_strided_ring<BP, INV, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RingCfg<BP, 1, 2>::SMEM);
@@ -124,7 +131,7 @@ int pipe_occupancy() {
 }
 int strided_ring(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s) {
     static_assert(PT == RingCfg<BP>::T, "the ring pass uses the tensor maps of the T = 8 tiles");
-    PipeArgs pa;
+    PipeArgs pa = {};
     pa.nzt = (a->nzv + PT - 1) / PT;
     pa.n_outer_eff = n_outer_eff;
     pa.total_tiles = pa.nzt * n_outer_eff * nfields;
@@ -134,19 +141,24 @@ int strided_ring(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer
     // SM (343 tiles) measured 1.39 ms per 3-field pass against 1.14 ms with runs of 6-12.  The run length is chosen so
     // that the CTAs fill whole waves of the max_ctas SMs as evenly as possible (small multi-GPU launches).
     static int tpc_max = 0;
-    if (tpc_max == 0) { const char* e = getenv("NSB200_RING_TPC"); tpc_max = e ? atoi(e) : 12; if (tpc_max < 1) tpc_max = 12; }
+    if (tpc_max == 0) { const char* e = getenv("NSB200_RING_TPC"); tpc_max = e ? atoi(e) : 8; if (tpc_max < 1) tpc_max = 8; }
     const int per_wave = max_ctas > 0 ? max_ctas : 148;
     const int waves = (pa.total_tiles + per_wave * tpc_max - 1) / (per_wave * tpc_max);
     pa.tiles_per_cta = (pa.total_tiles + per_wave * waves - 1) / (per_wave * waves);
     const int grid = (pa.total_tiles + pa.tiles_per_cta - 1) / pa.tiles_per_cta;
-    if (dir == FWD) k_fft_strided_ring<BP, FWD><<<grid, RingCfg<BP>::THREADS, RingCfg<BP>::SMEM, s>>>(*a, *maps, pa);
+    static int fr = -1;                 // free-running groups (default); NSB200_RING_FR=0 selects the slot-synchronised form
+    if (fr < 0) { const char* e = getenv("NSB200_RING_FR"); fr = (e && e[0] == '0') ? 0 : 1; }
+    if (fr) {
+        if (dir == FWD) k_fft_strided_ring_fr<BP, FWD><<<grid, RingCfg<BP>::THREADS, RingCfg<BP>::SMEM, s>>>(*a, *maps, pa);
+        else k_fft_strided_ring_fr<BP, INV><<<grid, RingCfg<BP>::THREADS, RingCfg<BP>::SMEM, s>>>(*a, *maps, pa);
+    } else if (dir == FWD) k_fft_strided_ring<BP, FWD><<<grid, RingCfg<BP>::THREADS, RingCfg<BP>::SMEM, s>>>(*a, *maps, pa);
     else k_fft_strided_ring<BP, INV><<<grid, RingCfg<BP>::THREADS, RingCfg<BP>::SMEM, s>>>(*a, *maps, pa);
     return (int)cudaGetLastError();
 }
 // light ring pass (one group, two buffers) on a restricted, persistent grid: the link-bound store phases of the overlapped schedule
 int strided_link(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s) {
     typedef RingCfg<BP, 1, 2> LC;
-    PipeArgs pa;
+    PipeArgs pa = {};
     pa.nzt = (a->nzv + PT - 1) / PT;
     pa.n_outer_eff = n_outer_eff;
     pa.total_tiles = pa.nzt * n_outer_eff * nfields;

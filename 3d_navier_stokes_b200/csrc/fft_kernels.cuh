@@ -1332,6 +1332,138 @@ __global__ void __launch_bounds__(RingCfg<P, NGROUP, NBUF_>::THREADS, 3 - NGROUP
 #endif
 }
 
+// Free-running form of the ring pass: the two groups are not tied to CTA-wide slots.  A group synchronises its own 256
+// threads between the passes of a tile with an mbarrier (arrive + parity wait); the hand-back of a tile buffer is a
+// split barrier: every thread arrives on the buffer's `empty` mbarrier right after its last shared-memory read and
+// carries on with its global stores, only the group's first thread waits for the 256 arrivals and re-issues the TMA.
+template <class P, int DIR>
+__global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring_fr(const StridedArgs a, const __grid_constant__ TmaMaps maps, const PipeArgs pa) {
+    typedef RingCfg<P> Cfg;
+    constexpr int T = Cfg::T, N = P::N, NBUF = Cfg::NBUF, GROUP = Cfg::GROUP, NGROUP = Cfg::NGROUP;
+    extern __shared__ __align__(1024) unsigned char nsb_smem_raw[];
+    cplx* smem = reinterpret_cast<cplx*>(nsb_smem_raw);
+    __shared__ __align__(8) unsigned long long s_bars[2 * NBUF + NGROUP];   // full[NBUF], empty[NBUF], group[NGROUP]
+    __shared__ long long s_delta[NSB_MAX_PEERS];
+    if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = a.peer_delta[threadIdx.x];
+    const int g = threadIdx.x / GROUP, tid = threadIdx.x % GROUP;
+    const int p = tid % T, q = tid / T;
+    const cplx* __restrict__ tw = a.tw;
+#ifdef __CUDA_ARCH__
+    const unsigned full0 = (unsigned)__cvta_generic_to_shared(&s_bars[0]);
+    const unsigned empty0 = full0 + 8u * NBUF;
+    const unsigned gbar = full0 + 8u * (2 * NBUF + g);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NBUF; ++i) { nsb_mbar_init(full0 + 8u * i, 1); nsb_mbar_init(empty0 + 8u * i, GROUP); }
+        for (int i = 0; i < NGROUP; ++i) nsb_mbar_init(full0 + 8u * (2 * NBUF + i), GROUP);
+    }
+    __syncthreads();
+    const int t0 = blockIdx.x * pa.tiles_per_cta;
+    const int t1 = (t0 + pa.tiles_per_cta < pa.total_tiles) ? t0 + pa.tiles_per_cta : pa.total_tiles;
+    const int nt = t1 - t0;
+    auto issue = [&](int t, int buf) {
+        const int kzt = t % pa.nzt, rest = t / pa.nzt;
+        int outer = rest % pa.n_outer_eff;
+        const int field = rest / pa.n_outer_eff;
+        if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
+        constexpr int ROWS = TmaChunk<N>::ROWS, COUNT = TmaChunk<N>::COUNT;
+        const unsigned bar = full0 + 8u * buf;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        nsb_mbar_expect_tx(bar, (unsigned)(N * T * sizeof(cplx)));
+#pragma unroll
+        for (int c = 0; c < COUNT; ++c) {
+            const bool use_hi = maps.pruned && (c >= COUNT / 2);
+            const void* mp = use_hi ? (const void*)&maps.hi[field] : (const void*)&maps.lo[field];
+            const int row = use_hi ? c * ROWS - maps.hi_row0 : c * ROWS;
+            nsb_tma_load_3d(sbase + (unsigned)((buf * N + c * ROWS) * T * sizeof(cplx)), mp, kzt * T * 2, row, outer, bar);
+        }
+    };
+    if (threadIdx.x == 0)
+        for (int i = 0; i < NBUF && i < nt; ++i) issue(t0 + i, i);
+    int bA, bB; bool self;
+    zw_lane_pair<P>(q, bA, bB, self);
+    const int tb = q ? q : P::M1 / 2;
+    const cplx w1a = tw[tb], w1b = tw[2 * tb], w1c = tw[4 * tb];
+    const cplx w2a = tw[P::R1 * (q % P::M2)], w2b = tw[P::R1 * (q % P::M2) * 2], w2c = tw[P::R1 * (q % P::M2) * 4];
+    const long long os1 = a.out_s1, os2 = a.out_s2;
+    const int osh = a.out_shift, omk = a.out_mask, slo = a.out_skip_lo, shi = a.out_skip_hi;
+    const int p2p = a.out_p2p, rank_lo = a.out_rank_lo;
+    unsigned gph = 0;                                  // parity of the group barrier's current phase
+    auto group_sync = [&]() {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar) : "memory");
+        nsb_mbar_wait(gbar, gph);
+        gph ^= 1u;
+    };
+    for (int it = g; it < nt; it += NGROUP) {
+        const int t = t0 + it;
+        const int buf = it % NBUF;
+        const unsigned par = (unsigned)((it / NBUF) & 1);
+        const int kzt = t % pa.nzt, rest = t / pa.nzt;
+        int outer = rest % pa.n_outer_eff;
+        const int field = rest / pa.n_outer_eff;
+        if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
+        const int kz = kzt * T + p;
+        const bool valid = kz < a.nzv;
+        cplx* dst = a.dst[field] + ((long long)outer * a.out_so + kz);
+        cplx* sm = smem + (size_t)buf * N * T + p;
+        // The two groups consume alternate phases of a buffer's barriers, and a parity wait cannot tell "the phase before
+        // mine is still open" from "mine is complete".  The previous tile of this buffer (it - NBUF, the other group's) has
+        // landed once its `empty` phase is complete; only then is the parity of `full` unambiguous.  (A fresh barrier
+        // passes a wait for parity 1, which covers the first NBUF tiles.)
+        nsb_mbar_wait(empty0 + 8u * buf, par ^ 1u);
+        nsb_mbar_wait(full0 + 8u * buf, par);
+        {
+            cplx v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = sm[(bA + j * P::M1) * T];
+            Dft<8, DIR>::run(v);
+            if (!self) twiddle8_base<DIR>(v, w1a, w1b, w1c);
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + bA) * T] = v[k1];
+        }
+        {
+            cplx y[8];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) y[n] = sm[(bB + ((n + 7) & 7) * P::M1) * T];
+            Dft<8, DIR>::run(y);
+            twiddle8_base<-DIR>(y, w1a, w1b, w1c);
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + bB) * T] = y[k1];
+        }
+        group_sync();
+        fft_pass2_r8_base<P, DIR, T>(q, sm, w2a, w2b, w2c);
+        fft_pass2_r8_base<P, DIR, T>(q + 32, sm, w2a, w2b, w2c);
+        group_sync();
+#pragma unroll 1
+        for (int b = q; b < P::NBL; b += 32) {
+            cplx v[P::RL];
+            fft_pass_last<P, DIR, T>(b, sm, v);
+            if (b + 32 >= P::NBL)                      // the thread's last read of the tile buffer
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * buf) : "memory");
+            if (valid) {
+#pragma unroll
+                for (int k2 = 0; k2 < P::RL; ++k2) {
+                    const int n = b + k2 * P::NBL;
+                    if (!(n >= slo && n < shi)) {
+                        if (p2p) {
+                            const int hi = n >> osh, lo = n & omk;
+                            cplx* d = reinterpret_cast<cplx*>(reinterpret_cast<char*>(dst) + s_delta[rank_lo ? lo : hi]);
+                            d[(long long)(rank_lo ? hi : lo) * os2] = v[k2];
+                        } else {
+                            dst[(long long)(n >> osh) * os1 + (long long)(n & omk) * os2] = v[k2];
+                        }
+                    }
+                }
+            }
+        }
+        if (tid == 0 && it + NBUF < nt) {
+            nsb_mbar_wait(empty0 + 8u * buf, par);
+            issue(t0 + it + NBUF, buf);
+        }
+    }
+#endif
+}
+
 // ------------------------------------------------------------------------------ launch helpers
 #ifndef NSB_STRIDED_TP_1024
 #define NSB_STRIDED_TP_1024 64

@@ -55,6 +55,31 @@ def test_tma_and_cp_async_tile_loads_are_bit_identical(n):
     assert h0 == h1
 
 
+def test_free_running_and_slot_synchronised_ring_passes_are_bit_identical():
+    """The free-running ring pass (per-group mbarriers, split buffer hand-back) runs the same butterflies as the
+    slot-synchronised form (NSB200_RING_FR=0); only the synchronisation differs, so not a bit may change - with the default
+    short runs per CTA and with one long run per SM, where the two groups drift furthest apart (the case in which a parity
+    wait on a barrier shared by both groups used to alias)."""
+    h0, e0 = run_variant(512, {})
+    h1, e1 = run_variant(512, {"NSB200_RING_FR": "0"})
+    h2, e2 = run_variant(512, {"NSB200_RING_TPC": "343"})
+    h3, e3 = run_variant(512, {"NSB200_RING_TPC": "3"})
+    assert h0 == h1 == h2 == h3 and e0 == e1 == e2 == e3
+
+
+def test_ring_pass_stress():
+    """A few thousand launches of the ring pass (single passes, transform pairs, full steps) with long runs per CTA: a lost
+    hand-shake shows up as a trap (bounded waits) or as a different final state than the default configuration."""
+    outs = []
+    for env_extra in ({}, {"NSB200_RING_TPC": "100"}):
+        env = dict(os.environ)
+        env.update(env_extra)
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ring_stress.py"), "512", "6"], env=env, capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        outs.append([l for l in p.stdout.splitlines() if l.startswith("stress ok")][-1])
+    assert outs[0] == outs[1]
+
+
 def test_strided_and_fused_z_kernel_generations_agree_to_rounding():
     """512^3: persistent ring pass vs one-shot strided pass, warp-per-transform fused z kernel vs the first generation.
     Same mathematics, different twiddle association: energies after two steps agree to 1e-13 (the fields themselves are
