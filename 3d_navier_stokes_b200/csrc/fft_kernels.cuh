@@ -4,9 +4,11 @@
 //   k_fft_strided   c2c pass along x or y: a CTA owns a tile of T consecutive kz columns
 //                   x N points, so every global access is T*16 contiguous bytes; tile-interleaved
 //                   shared memory ([element][T]) makes all exchanges conflict free.
-//   k_fft_strided_ring  the persistent form of that pass (N = 512): one CTA per SM, a TMA-fed ring of three tiles, two
-//                   slot-shifted groups of 256 threads; k_fft_strided_pipe: its single-group predecessor, still used on a
-//                   restricted grid for the link-bound store phases of the overlapped multi-GPU schedule.
+//   k_fft_strided_ring_fr  the ring form of that pass (N = 512): one CTA per SM, a TMA-fed ring of three tiles, two
+//                   free-running groups of 256 threads (mbarrier group sync, split-barrier buffer hand-back).
+//                   k_fft_strided_ring: its slot-synchronised predecessor (NSB200_RING_FR=0) and, with one group and two
+//                   buffers, the light kernel of the link-bound store phases of the overlapped multi-GPU schedule;
+//                   k_fft_strided_pipe: the single-group double-buffered form (NSB200_PIPE=1).
 //   k_z_c2r/k_z_r2c contiguous z pencils, two real pencils packed in one complex transform.
 //   k_z_fused       z c2r of (u, w) -> u x w -> z r2c in one kernel: the six real-space fields of a
 //                   pencil pair never leave the SM (reference loops solver.c:664-677 between the
