@@ -1209,6 +1209,92 @@ template <class P, int NGROUP_ = 2, int NBUF_ = 3> struct RingCfg {
 #endif
     static constexpr int SHIFT = NSB_RING_SHIFT;      // slots group 1 runs behind group 0
 };
+// ---- pieces shared by the two ring kernels
+// tile t of a launch: kz tile, outer index (the skipped range is stepped over) and field
+struct RingTile { int kzt, outer, field; };
+__device__ __forceinline__ RingTile ring_tile(int t, const PipeArgs& pa, const StridedArgs& a) {
+    RingTile r;
+    const int rest = t / pa.nzt;
+    r.kzt = t % pa.nzt;
+    r.outer = rest % pa.n_outer_eff;
+    r.field = rest / pa.n_outer_eff;
+    if (r.outer >= a.outer_lo) r.outer += a.outer_hi - a.outer_lo;
+    return r;
+}
+#ifdef __CUDA_ARCH__
+// request a tile into the buffer at shared address `dst` (one elected thread): TmaChunk<N>::COUNT boxes on the `full` barrier
+template <int N, int T> __device__ __forceinline__ void ring_issue(const RingTile& tl, unsigned dst, unsigned bar, const TmaMaps& maps) {
+    constexpr int ROWS = TmaChunk<N>::ROWS, COUNT = TmaChunk<N>::COUNT;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last touched through the generic proxy
+    nsb_mbar_expect_tx(bar, (unsigned)(N * T * sizeof(cplx)));
+#pragma unroll
+    for (int c = 0; c < COUNT; ++c) {
+        const bool use_hi = maps.pruned && (c >= COUNT / 2);
+        const void* mp = use_hi ? (const void*)&maps.hi[tl.field] : (const void*)&maps.lo[tl.field];
+        const int row = use_hi ? c * ROWS - maps.hi_row0 : c * ROWS;
+        nsb_tma_load_3d(dst + (unsigned)(c * ROWS * T * sizeof(cplx)), mp, tl.kzt * T * 2, row, tl.outer, bar);
+    }
+}
+#endif
+// per-thread constants of the ring pass: the mirrored pass-1 pair (q, 64 - q) with the powers 1, 2, 4 of its base twiddle
+// (see zw_load_tw1) and those of the pass-2 butterflies q, q + 32; the other powers are formed on the fly
+template <class P> struct RingLane {
+    int bA, bB; bool self;
+    cplx w1a, w1b, w1c, w2a, w2b, w2c;
+    __device__ __forceinline__ RingLane(int q, const cplx* __restrict__ tw) {
+        zw_lane_pair<P>(q, bA, bB, self);
+        const int tb = q ? q : P::M1 / 2, m2 = q % P::M2;
+        w1a = tw[tb]; w1b = tw[2 * tb]; w1c = tw[4 * tb];
+        w2a = tw[P::R1 * m2]; w2b = tw[P::R1 * m2 * 2]; w2c = tw[P::R1 * m2 * 4];
+    }
+};
+// pass 1 of the pair in place: butterfly bA, then its mirror image bB (inputs shifted by one, conjugated twiddles: zw_bfly_pair)
+template <class P, int DIR, int T> __device__ __forceinline__ void ring_pass1(cplx* sm, const RingLane<P>& L) {
+    {
+        cplx v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = sm[(L.bA + j * P::M1) * T];
+        Dft<8, DIR>::run(v);
+        if (!L.self) twiddle8_base<DIR>(v, L.w1a, L.w1b, L.w1c);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + L.bA) * T] = v[k1];
+    }
+    {
+        cplx y[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) y[n] = sm[(L.bB + ((n + 7) & 7) * P::M1) * T];
+        Dft<8, DIR>::run(y);
+        twiddle8_base<-DIR>(y, L.w1a, L.w1b, L.w1c);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + L.bB) * T] = y[k1];
+    }
+}
+// where the outputs of a tile column go (natural layout, per-destination blocks, or straight into the peers' slabs)
+struct RingOut {
+    long long os1, os2;
+    int osh, omk, slo, shi, p2p, rank_lo;
+    const long long* delta;       // shared-memory copy of peer_delta
+    __device__ __forceinline__ RingOut(const StridedArgs& a, const long long* d)
+        : os1(a.out_s1), os2(a.out_s2), osh(a.out_shift), omk(a.out_mask), slo(a.out_skip_lo), shi(a.out_skip_hi), p2p(a.out_p2p), rank_lo(a.out_rank_lo), delta(d) {}
+    // outputs n = b + k2 * NBL of last-pass butterfly b
+    template <class P> __device__ __forceinline__ void store(cplx* dst, int b, const cplx* v) const {
+#pragma unroll
+        for (int k2 = 0; k2 < P::RL; ++k2) {
+            const int n = b + k2 * P::NBL;
+            if (!(n >= slo && n < shi)) {
+                if (p2p) {
+                    const int hi = n >> osh, lo = n & omk;
+                    cplx* d = reinterpret_cast<cplx*>(reinterpret_cast<char*>(dst) + delta[rank_lo ? lo : hi]);
+                    d[(long long)(rank_lo ? hi : lo) * os2] = v[k2];
+                } else {
+                    dst[(long long)(n >> osh) * os1 + (long long)(n & omk) * os2] = v[k2];
+                }
+            }
+        }
+    }
+};
+
+// Slot-synchronised form (NSB200_RING_FR=0; with NGROUP = 1, NBUF = 2 the light kernel of the link-bound store phases).
 template <class P, int DIR, int NGROUP = 2, int NBUF_ = 3>
 __global__ void __launch_bounds__(RingCfg<P, NGROUP, NBUF_>::THREADS, 3 - NGROUP) k_fft_strided_ring(const StridedArgs a, const __grid_constant__ TmaMaps maps, const PipeArgs pa) {
     typedef RingCfg<P, NGROUP, NBUF_> Cfg;
@@ -1220,7 +1306,6 @@ __global__ void __launch_bounds__(RingCfg<P, NGROUP, NBUF_>::THREADS, 3 - NGROUP
     if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = a.peer_delta[threadIdx.x];
     const int g = threadIdx.x / GROUP, tid = threadIdx.x % GROUP;
     const int p = tid % T, q = tid / T;               // column of the tile, butterfly index 0..31
-    const cplx* __restrict__ tw = a.tw;
 #ifdef __CUDA_ARCH__
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
@@ -1231,35 +1316,11 @@ __global__ void __launch_bounds__(RingCfg<P, NGROUP, NBUF_>::THREADS, 3 - NGROUP
     const int t0 = blockIdx.x * pa.tiles_per_cta;
     const int t1 = (t0 + pa.tiles_per_cta < pa.total_tiles) ? t0 + pa.tiles_per_cta : pa.total_tiles;
     const int nt = t1 - t0;
-    auto issue = [&](int t, int buf) {
-        const int kzt = t % pa.nzt, rest = t / pa.nzt;
-        int outer = rest % pa.n_outer_eff;
-        const int field = rest / pa.n_outer_eff;
-        if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
-        constexpr int ROWS = TmaChunk<N>::ROWS, COUNT = TmaChunk<N>::COUNT;
-        const unsigned bar = bar0 + 8u * buf;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last touched through the generic proxy
-        nsb_mbar_expect_tx(bar, (unsigned)(N * T * sizeof(cplx)));
-#pragma unroll
-        for (int c = 0; c < COUNT; ++c) {
-            const bool use_hi = maps.pruned && (c >= COUNT / 2);
-            const void* mp = use_hi ? (const void*)&maps.hi[field] : (const void*)&maps.lo[field];
-            const int row = use_hi ? c * ROWS - maps.hi_row0 : c * ROWS;
-            nsb_tma_load_3d(sbase + (unsigned)((buf * N + c * ROWS) * T * sizeof(cplx)), mp, kzt * T * 2, row, outer, bar);
-        }
-    };
+    auto issue = [&](int t, int buf) { ring_issue<N, T>(ring_tile(t, pa, a), sbase + (unsigned)(buf * N * T * sizeof(cplx)), bar0 + 8u * buf, maps); };
     if (threadIdx.x == 0)
         for (int i = 0; i < NBUF && i < nt; ++i) issue(t0 + i, i);
-    int bA, bB; bool self;
-    zw_lane_pair<P>(q, bA, bB, self);
-    // twiddles of the pair (see zw_load_tw1) and of the two pass-2 butterflies q, q + 32: the powers 1, 2, 4 stay in
-    // registers, the others are formed on the fly
-    const int tb = q ? q : P::M1 / 2;
-    const cplx w1a = tw[tb], w1b = tw[2 * tb], w1c = tw[4 * tb];
-    const cplx w2a = tw[P::R1 * (q % P::M2)], w2b = tw[P::R1 * (q % P::M2) * 2], w2c = tw[P::R1 * (q % P::M2) * 4];
-    const long long os1 = a.out_s1, os2 = a.out_s2;
-    const int osh = a.out_shift, omk = a.out_mask, slo = a.out_skip_lo, shi = a.out_skip_hi;
-    const int p2p = a.out_p2p, rank_lo = a.out_rank_lo;
+    const RingLane<P> L(q, a.tw);
+    const RingOut out(a, s_delta);
     // Time is cut into slots separated by CTA barriers; a group spends three consecutive slots on a tile (pass 1, pass 2,
     // last pass + stores) and group 1 runs SHIFT slots behind group 0, so the two groups are always in different passes.
     const int ntg = (nt - g + NGROUP - 1) / NGROUP;    // tiles of this group: it = g, g + NGROUP, ...
@@ -1274,58 +1335,23 @@ __global__ void __launch_bounds__(RingCfg<P, NGROUP, NBUF_>::THREADS, 3 - NGROUP
         const int ph = active ? ls % 3 : -1;
         const int it = g + NGROUP * (ls / 3);
         if (ph == 0) {
-            const int t = t0 + it;
+            const RingTile tl = ring_tile(t0 + it, pa, a);
             buf = it % NBUF;
-            const int kzt = t % pa.nzt, rest = t / pa.nzt;
-            int outer = rest % pa.n_outer_eff;
-            const int field = rest / pa.n_outer_eff;
-            if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
-            const int kz = kzt * T + p;
+            const int kz = tl.kzt * T + p;
             valid = kz < a.nzv;
-            dst = a.dst[field] + ((long long)outer * a.out_so + kz);
+            dst = a.dst[tl.field] + ((long long)tl.outer * a.out_so + kz);
             sm = smem + (size_t)buf * N * T + p;
             nsb_mbar_wait(bar0 + 8u * buf, (unsigned)((it / NBUF) & 1));
-            {   // pass 1 in place: butterfly bA ...
-                cplx v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = sm[(bA + j * P::M1) * T];
-                Dft<8, DIR>::run(v);
-                if (!self) twiddle8_base<DIR>(v, w1a, w1b, w1c);
-#pragma unroll
-                for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + bA) * T] = v[k1];
-            }
-            {   // ... and its mirror image bB: inputs shifted by one, conjugated twiddles (zw_bfly_pair)
-                cplx y[8];
-#pragma unroll
-                for (int n = 0; n < 8; ++n) y[n] = sm[(bB + ((n + 7) & 7) * P::M1) * T];
-                Dft<8, DIR>::run(y);
-                twiddle8_base<-DIR>(y, w1a, w1b, w1c);
-#pragma unroll
-                for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + bB) * T] = y[k1];
-            }
+            ring_pass1<P, DIR, T>(sm, L);
         } else if (ph == 1) {
-            fft_pass2_r8_base<P, DIR, T>(q, sm, w2a, w2b, w2c);
-            fft_pass2_r8_base<P, DIR, T>(q + 32, sm, w2a, w2b, w2c);
+            fft_pass2_r8_base<P, DIR, T>(q, sm, L.w2a, L.w2b, L.w2c);
+            fft_pass2_r8_base<P, DIR, T>(q + 32, sm, L.w2a, L.w2b, L.w2c);
         } else if (ph == 2) {
 #pragma unroll 1
             for (int b = q; b < P::NBL; b += 32) {
                 cplx v[P::RL];
                 fft_pass_last<P, DIR, T>(b, sm, v);
-                if (valid) {
-#pragma unroll
-                    for (int k2 = 0; k2 < P::RL; ++k2) {
-                        const int n = b + k2 * P::NBL;
-                        if (!(n >= slo && n < shi)) {
-                            if (p2p) {
-                                const int hi = n >> osh, lo = n & omk;
-                                cplx* d = reinterpret_cast<cplx*>(reinterpret_cast<char*>(dst) + s_delta[rank_lo ? lo : hi]);
-                                d[(long long)(rank_lo ? hi : lo) * os2] = v[k2];
-                            } else {
-                                dst[(long long)(n >> osh) * os1 + (long long)(n & omk) * os2] = v[k2];
-                            }
-                        }
-                    }
-                }
+                if (valid) out.template store<P>(dst, b, v);
             }
         }
         __syncthreads();
@@ -1334,10 +1360,11 @@ __global__ void __launch_bounds__(RingCfg<P, NGROUP, NBUF_>::THREADS, 3 - NGROUP
 #endif
 }
 
-// Free-running form of the ring pass: the two groups are not tied to CTA-wide slots.  A group synchronises its own 256
-// threads between the passes of a tile with an mbarrier (arrive + parity wait); the hand-back of a tile buffer is a
-// split barrier: every thread arrives on the buffer's `empty` mbarrier right after its last shared-memory read and
-// carries on with its global stores, only the group's first thread waits for the 256 arrivals and re-issues the TMA.
+// Free-running form of the ring pass (the default): the two groups are not tied to CTA-wide slots.  A group synchronises
+// its own 256 threads between the passes of a tile with an mbarrier (arrive + parity wait); the hand-back of a tile
+// buffer is a split barrier: every thread arrives on the buffer's `empty` mbarrier right after its last shared-memory
+// read and carries on with its global stores, only the group's first thread waits for the 256 arrivals and re-issues
+// the TMA.
 template <class P, int DIR>
 __global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring_fr(const StridedArgs a, const __grid_constant__ TmaMaps maps, const PipeArgs pa) {
     typedef RingCfg<P> Cfg;
@@ -1349,7 +1376,6 @@ __global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring_fr(
     if (threadIdx.x < NSB_MAX_PEERS) s_delta[threadIdx.x] = a.peer_delta[threadIdx.x];
     const int g = threadIdx.x / GROUP, tid = threadIdx.x % GROUP;
     const int p = tid % T, q = tid / T;
-    const cplx* __restrict__ tw = a.tw;
 #ifdef __CUDA_ARCH__
     const unsigned full0 = (unsigned)__cvta_generic_to_shared(&s_bars[0]);
     const unsigned empty0 = full0 + 8u * NBUF;
@@ -1363,33 +1389,11 @@ __global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring_fr(
     const int t0 = blockIdx.x * pa.tiles_per_cta;
     const int t1 = (t0 + pa.tiles_per_cta < pa.total_tiles) ? t0 + pa.tiles_per_cta : pa.total_tiles;
     const int nt = t1 - t0;
-    auto issue = [&](int t, int buf) {
-        const int kzt = t % pa.nzt, rest = t / pa.nzt;
-        int outer = rest % pa.n_outer_eff;
-        const int field = rest / pa.n_outer_eff;
-        if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
-        constexpr int ROWS = TmaChunk<N>::ROWS, COUNT = TmaChunk<N>::COUNT;
-        const unsigned bar = full0 + 8u * buf;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        nsb_mbar_expect_tx(bar, (unsigned)(N * T * sizeof(cplx)));
-#pragma unroll
-        for (int c = 0; c < COUNT; ++c) {
-            const bool use_hi = maps.pruned && (c >= COUNT / 2);
-            const void* mp = use_hi ? (const void*)&maps.hi[field] : (const void*)&maps.lo[field];
-            const int row = use_hi ? c * ROWS - maps.hi_row0 : c * ROWS;
-            nsb_tma_load_3d(sbase + (unsigned)((buf * N + c * ROWS) * T * sizeof(cplx)), mp, kzt * T * 2, row, outer, bar);
-        }
-    };
+    auto issue = [&](int t, int buf) { ring_issue<N, T>(ring_tile(t, pa, a), sbase + (unsigned)(buf * N * T * sizeof(cplx)), full0 + 8u * buf, maps); };
     if (threadIdx.x == 0)
         for (int i = 0; i < NBUF && i < nt; ++i) issue(t0 + i, i);
-    int bA, bB; bool self;
-    zw_lane_pair<P>(q, bA, bB, self);
-    const int tb = q ? q : P::M1 / 2;
-    const cplx w1a = tw[tb], w1b = tw[2 * tb], w1c = tw[4 * tb];
-    const cplx w2a = tw[P::R1 * (q % P::M2)], w2b = tw[P::R1 * (q % P::M2) * 2], w2c = tw[P::R1 * (q % P::M2) * 4];
-    const long long os1 = a.out_s1, os2 = a.out_s2;
-    const int osh = a.out_shift, omk = a.out_mask, slo = a.out_skip_lo, shi = a.out_skip_hi;
-    const int p2p = a.out_p2p, rank_lo = a.out_rank_lo;
+    const RingLane<P> L(q, a.tw);
+    const RingOut out(a, s_delta);
     unsigned gph = 0;                                  // parity of the group barrier's current phase
     auto group_sync = [&]() {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar) : "memory");
@@ -1397,16 +1401,12 @@ __global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring_fr(
         gph ^= 1u;
     };
     for (int it = g; it < nt; it += NGROUP) {
-        const int t = t0 + it;
+        const RingTile tl = ring_tile(t0 + it, pa, a);
         const int buf = it % NBUF;
         const unsigned par = (unsigned)((it / NBUF) & 1);
-        const int kzt = t % pa.nzt, rest = t / pa.nzt;
-        int outer = rest % pa.n_outer_eff;
-        const int field = rest / pa.n_outer_eff;
-        if (outer >= a.outer_lo) outer += a.outer_hi - a.outer_lo;
-        const int kz = kzt * T + p;
+        const int kz = tl.kzt * T + p;
         const bool valid = kz < a.nzv;
-        cplx* dst = a.dst[field] + ((long long)outer * a.out_so + kz);
+        cplx* dst = a.dst[tl.field] + ((long long)tl.outer * a.out_so + kz);
         cplx* sm = smem + (size_t)buf * N * T + p;
         // The two groups consume alternate phases of a buffer's barriers, and a parity wait cannot tell "the phase before
         // mine is still open" from "mine is complete".  The previous tile of this buffer (it - NBUF, the other group's) has
@@ -1414,27 +1414,10 @@ __global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring_fr(
         // passes a wait for parity 1, which covers the first NBUF tiles.)
         nsb_mbar_wait(empty0 + 8u * buf, par ^ 1u);
         nsb_mbar_wait(full0 + 8u * buf, par);
-        {
-            cplx v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = sm[(bA + j * P::M1) * T];
-            Dft<8, DIR>::run(v);
-            if (!self) twiddle8_base<DIR>(v, w1a, w1b, w1c);
-#pragma unroll
-            for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + bA) * T] = v[k1];
-        }
-        {
-            cplx y[8];
-#pragma unroll
-            for (int n = 0; n < 8; ++n) y[n] = sm[(bB + ((n + 7) & 7) * P::M1) * T];
-            Dft<8, DIR>::run(y);
-            twiddle8_base<-DIR>(y, w1a, w1b, w1c);
-#pragma unroll
-            for (int k1 = 0; k1 < 8; ++k1) sm[(k1 * P::M1 + bB) * T] = y[k1];
-        }
+        ring_pass1<P, DIR, T>(sm, L);
         group_sync();
-        fft_pass2_r8_base<P, DIR, T>(q, sm, w2a, w2b, w2c);
-        fft_pass2_r8_base<P, DIR, T>(q + 32, sm, w2a, w2b, w2c);
+        fft_pass2_r8_base<P, DIR, T>(q, sm, L.w2a, L.w2b, L.w2c);
+        fft_pass2_r8_base<P, DIR, T>(q + 32, sm, L.w2a, L.w2b, L.w2c);
         group_sync();
 #pragma unroll 1
         for (int b = q; b < P::NBL; b += 32) {
@@ -1442,21 +1425,7 @@ __global__ void __launch_bounds__(RingCfg<P>::THREADS, 1) k_fft_strided_ring_fr(
             fft_pass_last<P, DIR, T>(b, sm, v);
             if (b + 32 >= P::NBL)                      // the thread's last read of the tile buffer
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * buf) : "memory");
-            if (valid) {
-#pragma unroll
-                for (int k2 = 0; k2 < P::RL; ++k2) {
-                    const int n = b + k2 * P::NBL;
-                    if (!(n >= slo && n < shi)) {
-                        if (p2p) {
-                            const int hi = n >> osh, lo = n & omk;
-                            cplx* d = reinterpret_cast<cplx*>(reinterpret_cast<char*>(dst) + s_delta[rank_lo ? lo : hi]);
-                            d[(long long)(rank_lo ? hi : lo) * os2] = v[k2];
-                        } else {
-                            dst[(long long)(n >> osh) * os1 + (long long)(n & omk) * os2] = v[k2];
-                        }
-                    }
-                }
-            }
+            if (valid) out.template store<P>(dst, b, v);
         }
         if (tid == 0 && it + NBUF < nt) {
             nsb_mbar_wait(empty0 + 8u * buf, par);
