@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 measurement campaign, one GPU: bench line, ncu launch list of the same command, full captures of the top kernels
+# measurement campaign, one GPU (gpurun -- bash scripts/campaign_1gpu.sh): bench line, ncu launch list of the same command, full captures of the top kernels
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 ( time timeout 1500 python bench.py --steps 20 --warmup 3 ) > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err

@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU check: two-rank tests (when N == 2) and the bench line with its parity pre-check
+# multi-GPU campaign (gpurun --gpus N -- bash scripts/campaign_multi_gpu.sh N): two-rank tests (N == 2) and the bench line with its parity pre-check
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 N=$1
