@@ -175,6 +175,12 @@ template <> struct ZFPlan<256> { typedef FftPlan<256, 8, 4, 8> type; };
 template <> struct ZFPlan<512> { typedef FftPlan<512, 8, 8, 8> type; };
 template <> struct ZFPlan<1024> { typedef FftPlan<1024, 8, 4, 4, 1, 8> type; };   // 4 passes, radix <= 8 (the radix-16 plan needed 168 registers)
 
+// plans of the stand-alone warp-per-pair z passes (k_z_c2r_w / k_z_r2c_w): 8 x R2 x 8, M1 = N/8 butterflies per pass
+template <int N> struct ZWPlan { typedef void type; };
+template <> struct ZWPlan<128> { typedef FftPlan<128, 8, 2, 8> type; };
+template <> struct ZWPlan<256> { typedef FftPlan<256, 8, 4, 8> type; };
+template <> struct ZWPlan<512> { typedef FftPlan<512, 8, 8, 8> type; };
+
 template <class P> NSB_HD int padi(int i) { return (i / P::M1) * P::ROW + i % P::M1; }
 
 // ---------------------------------------------------------------------------------------------
@@ -362,6 +368,38 @@ template <int DIR> NSB_HD void twiddle8_base(cplx* v, cplx wa, cplx wb, cplx wc)
     v[7] = cmul_dir<DIR>(v[7], cmul(w3, wc));
     v[5] = cmul_dir<DIR>(v[5], cmul(wa, wc));
     v[6] = cmul_dir<DIR>(v[6], cmul(wb, wc));
+}
+
+// radix-2 mid pass
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass2_r2_base(int b, cplx* sm, cplx wa) {
+    static_assert(P::PASSES >= 3 && P::R2 == 2, "radix-2 pass 2");
+    const int k1 = b / P::M2, m2 = b % P::M2;
+    const int base = k1 * P::ROW + m2;
+    cplx v[2];
+    v[0] = sm[base * STRIDE];
+    v[1] = sm[(base + P::M2) * STRIDE];
+    Dft<2, DIR>::run(v);
+    v[1] = cmul_dir<DIR>(v[1], wa);
+    sm[base * STRIDE] = v[0];
+    sm[(base + P::M2) * STRIDE] = v[1];
+}
+
+// radix-4 mid pass, twiddles W^{R1 m2 kp} from the powers 1 and 2
+template <class P, int DIR, int STRIDE>
+NSB_HD void fft_pass2_r4_base(int b, cplx* sm, cplx wa, cplx wb) {
+    static_assert(P::PASSES >= 3 && P::R2 == 4, "radix-4 pass 2");
+    const int k1 = b / P::M2, m2 = b % P::M2;
+    const int base = k1 * P::ROW + m2;
+    cplx v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = sm[(base + j * P::M2) * STRIDE];
+    Dft<4, DIR>::run(v);
+    v[1] = cmul_dir<DIR>(v[1], wa);
+    v[2] = cmul_dir<DIR>(v[2], wb);
+    v[3] = cmul_dir<DIR>(v[3], cmul(wa, wb));
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) sm[(base + kp * P::M2) * STRIDE] = v[kp];
 }
 
 // radix-16 mid pass with the fifteen twiddle powers formed on the fly from W^1, W^2, W^4, W^8 (16 registers instead of 60)

@@ -18,6 +18,13 @@
 #else
 #define NSB_HAVE_ZFW 0
 #endif
+// the stand-alone warp-per-pair z passes also exist for 256 = 8 x 4 x 8 and 128 = 8 x 2 x 8 (two / four pencil pairs side by
+// side in a warp)
+#if NSB_N == 512 || NSB_N == 256 || NSB_N == 128
+#define NSB_HAVE_ZPW 1
+#else
+#define NSB_HAVE_ZPW 0
+#endif
 // ... and in its general form (two mirrored pairs per lane, radix-16 middle pass) for 1024 = 8 x 16 x 8
 #if NSB_N == 1024
 #define NSB_HAVE_ZG 1
@@ -29,6 +36,9 @@ namespace {
 typedef BigPlan<NSB_N>::type BP;
 typedef ZPlan<NSB_N>::type ZP;
 typedef ZFPlan<NSB_N>::type ZF;
+#if NSB_HAVE_ZPW
+typedef ZWPlan<NSB_N>::type ZW;
+#endif
 #if NSB_HAVE_ZG
 typedef FftPlan<NSB_N, 8, 16, 8> ZG;
 #endif
@@ -56,11 +66,14 @@ int setup() {
     e = cudaFuncSetAttribute(k_z_fused<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZFusedSmem);
     if (e != cudaSuccess) return (int)e;
 #if NSB_HAVE_ZFW
+    if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_z_fused_w<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpCfg<ZF>::SMEM);
+#endif
+#if NSB_HAVE_ZPW
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_z_c2r_w<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpPassCfg<ZF>::SMEM);
+    e = cudaFuncSetAttribute(k_z_c2r_w<ZW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpPassCfg<ZW>::SMEM);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_z_r2c_w<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpPassCfg<ZF>::SMEM);
+    e = cudaFuncSetAttribute(k_z_r2c_w<ZW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpPassCfg<ZW>::SMEM);
 #endif
 #if NSB_HAVE_ZG
     if (e != cudaSuccess) return (int)e;
@@ -191,8 +204,10 @@ int zlaunch(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s) 
     else if (which == NSB_Z_R2C) k_z_r2c<ZP><<<dim3(grid_x, nfields), TH, kZSmem, s>>>(*a);
 #if NSB_HAVE_ZFW
     else if (which == NSB_Z_FUSED_W) k_z_fused_w<ZF><<<dim3(grid_x), ZWarpCfg<ZF>::THREADS, ZWarpCfg<ZF>::SMEM, s>>>(*a);
-    else if (which == NSB_Z_C2R_W) k_z_c2r_w<ZF><<<dim3(grid_x, nfields), ZWarpPassCfg<ZF>::THREADS, ZWarpPassCfg<ZF>::SMEM, s>>>(*a);
-    else if (which == NSB_Z_R2C_W) k_z_r2c_w<ZF><<<dim3(grid_x, nfields), ZWarpPassCfg<ZF>::THREADS, ZWarpPassCfg<ZF>::SMEM, s>>>(*a);
+#endif
+#if NSB_HAVE_ZPW
+    else if (which == NSB_Z_C2R_W) k_z_c2r_w<ZW><<<dim3(grid_x, nfields), ZWarpPassCfg<ZW>::THREADS, ZWarpPassCfg<ZW>::SMEM, s>>>(*a);
+    else if (which == NSB_Z_R2C_W) k_z_r2c_w<ZW><<<dim3(grid_x, nfields), ZWarpPassCfg<ZW>::THREADS, ZWarpPassCfg<ZW>::SMEM, s>>>(*a);
 #endif
 #if NSB_HAVE_ZG
     else if (which == NSB_Z_FUSED_W) k_zg_fused<ZG><<<dim3(grid_x), ZGenCfg<ZG>::FUSED_THREADS, ZGenCfg<ZG>::FUSED_SMEM, s>>>(*a);
@@ -210,8 +225,10 @@ int zocc(int which) {
     else if (which == NSB_Z_R2C) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_r2c<ZP>, TH, kZSmem);
 #if NSB_HAVE_ZFW
     else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused_w<ZF>, ZWarpCfg<ZF>::THREADS, ZWarpCfg<ZF>::SMEM);
-    else if (which == NSB_Z_C2R_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_c2r_w<ZF>, ZWarpPassCfg<ZF>::THREADS, ZWarpPassCfg<ZF>::SMEM);
-    else if (which == NSB_Z_R2C_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_r2c_w<ZF>, ZWarpPassCfg<ZF>::THREADS, ZWarpPassCfg<ZF>::SMEM);
+#endif
+#if NSB_HAVE_ZPW
+    else if (which == NSB_Z_C2R_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_c2r_w<ZW>, ZWarpPassCfg<ZW>::THREADS, ZWarpPassCfg<ZW>::SMEM);
+    else if (which == NSB_Z_R2C_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_r2c_w<ZW>, ZWarpPassCfg<ZW>::THREADS, ZWarpPassCfg<ZW>::SMEM);
 #endif
 #if NSB_HAVE_ZG
     else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zg_fused<ZG>, ZGenCfg<ZG>::FUSED_THREADS, ZGenCfg<ZG>::FUSED_SMEM);
@@ -223,7 +240,15 @@ int zocc(int which) {
 }
 }  // namespace
 
+// pencil pairs per CTA of the stand-alone warp passes (0: not built for this N)
+#if NSB_HAVE_ZPW
+#define NSB_ZPW_PAIRS ZWarpPassCfg<ZW>::PAIRS
+#elif NSB_HAVE_ZG
+#define NSB_ZPW_PAIRS 4
+#else
+#define NSB_ZPW_PAIRS 0
+#endif
 extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, NSB_PIPE_TCOLS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G,
      // 1024: the general fused kernel (249 registers, 2 x 3 warps per SM) measured slower than the first generation (117.5 vs 108.8 ms
      // per step), the stand-alone passes faster (65 vs 56 % of the HBM peak): NSB200_ZF=warp still selects it for experiments
-     NSB_HAVE_ZFW ? 1 : (NSB_HAVE_ZG ? -1 : 0), (NSB_HAVE_ZFW || NSB_HAVE_ZG) ? 4 : 0, (NSB_HAVE_ZFW || NSB_HAVE_ZG) ? 4 : 0}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC, NSB_RING_FN, NSB_LINK_FN};
+     NSB_HAVE_ZFW ? 1 : (NSB_HAVE_ZG ? -1 : 0), NSB_ZPW_PAIRS, NSB_ZPW_PAIRS}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC, NSB_RING_FN, NSB_LINK_FN};

@@ -827,64 +827,90 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
 }
 
 // Stand-alone z passes (3-D transform API, initial conditions, real-space dumps, the FFT sweep), one warp per pencil
-// pair with the same lane helpers as k_z_fused_w: no CTA barrier at all, every warp walks its own pairs.
-template <class P> struct ZWarpPassCfg { static constexpr int WARPS = 4, THREADS = 32 * WARPS, SMEM = WARPS * P::NPAD * 16; };
+// pair with the same lane helpers as k_z_fused_w: no CTA barrier at all, every warp walks its own pairs.  A plan with
+// M1 = 32 or 16 butterflies per pass (N = 256 = 8 x 4 x 8, N = 128 = 8 x 2 x 8) needs only 16 or 8 lanes per transform:
+// the warp then transforms SUB = 2 or 4 pencil pairs side by side, each in its own buffer.
+template <class P> struct ZWarpPassCfg {
+    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && (P::M1 == 64 || P::M1 == 32 || P::M1 == 16) && P::M2 == 8,
+                  "warp-per-pair z passes: plan 8 x (8 | 4 | 2) x 8");
+    static constexpr int LPT = P::M1 / 2;             // lanes per transform: lane l owns the mirrored pair (l, M1 - l)
+    static constexpr int SUB = 32 / LPT;              // transforms side by side in a warp
+    static constexpr int WARPS = 4, THREADS = 32 * WARPS, PAIRS = WARPS * SUB, SMEM = PAIRS * P::NPAD * 16;
+};
+// middle pass by the LPT lanes of a transform: NB2 / LPT butterflies per lane, all with the lane's m2 = l % 8
+template <class P, int DIR> NSB_HD void zw_pass2(int l, cplx* buf, cplx w2a, cplx w2b, cplx w2c) {
+    constexpr int LPT = ZWarpPassCfg<P>::LPT;
+#pragma unroll
+    for (int i = 0; i < P::NB2 / LPT; ++i) {
+        if constexpr (P::R2 == 8) fft_pass2_r8_base<P, DIR, 1>(l + LPT * i, buf, w2a, w2b, w2c);
+        else if constexpr (P::R2 == 4) fft_pass2_r4_base<P, DIR, 1>(l + LPT * i, buf, w2a, w2b);
+        else fft_pass2_r2_base<P, DIR, 1>(l + LPT * i, buf, w2a);
+    }
+}
 
 template <class P>
 __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const ZArgs a) {
-    constexpr int N = P::N, WARPS = ZWarpPassCfg<P>::WARPS;
+    typedef ZWarpPassCfg<P> Cfg;
+    constexpr int LPT = Cfg::LPT, SUB = Cfg::SUB;
     extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
     const int wp = threadIdx.x >> 5, L = threadIdx.x & 31;
-    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + wp * P::NPAD;
+    const int l = L % LPT, sub = L / LPT;
+    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + (wp * SUB + sub) * P::NPAD;
     cplx* F = a.base + (long long)blockIdx.y * a.fstride;
     const cplx* __restrict__ tw = a.tw;
     const int kzin = a.kz_in;
     int bA, bB; bool self;
-    zw_lane_pair<P>(L, bA, bB, self);
+    zw_lane_pair<P>(l, bA, bB, self);
     cplx w1[7];
-    zw_load_tw1<P>(L, tw, w1);
-    const cplx w2a = tw[P::R1 * (L % P::M2)], w2b = tw[P::R1 * (L % P::M2) * 2], w2c = tw[P::R1 * (L % P::M2) * 4];   // see k_z_fused_w
-    for (long long pr = (long long)blockIdx.x * WARPS + wp; pr < a.npairs; pr += (long long)gridDim.x * WARPS) {
-        cplx* ra = F + 2 * pr * a.rs;
+    zw_load_tw1<P>(l, tw, w1);
+    const cplx w2a = tw[P::R1 * (l % P::M2)], w2b = tw[P::R1 * (l % P::M2) * 2], w2c = tw[P::R1 * (l % P::M2) * 4];   // see k_z_fused_w
+    for (long long p0 = ((long long)blockIdx.x * Cfg::WARPS + wp) * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * Cfg::PAIRS) {
+        const long long pr = p0 + sub;
+        const bool ok = pr < a.npairs;                   // the last warp trip may hold fewer than SUB pairs
+        cplx* ra = F + 2 * (ok ? pr : p0) * a.rs;
         cplx* rb = ra + a.rs;
-        zw_inv_pass1<P>(L, buf, w1, [&](int k, cplx& A, cplx& B) {
-            if (k < kzin) { A = NSB_LDCG(ra + k); B = NSB_LDCG(rb + k); }
+        zw_inv_pass1<P>(l, buf, w1, [&](int k, cplx& A, cplx& B) {
+            if (k < kzin && ok) { A = NSB_LDCG(ra + k); B = NSB_LDCG(rb + k); }
             else { A = mk(0.0, 0.0); B = mk(0.0, 0.0); }
         });
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r8_base<P, INV, 1>(L + 32 * i, buf, w2a, w2b, w2c);
+        zw_pass2<P, INV>(l, buf, w2a, w2b, w2c);
         __syncwarp();
         cplx va[8], vb[8];
-        zw_last_pair<P, INV>(L, buf, va, vb);
-        double* oa = reinterpret_cast<double*>(ra);      // in place: the real rows reuse the half-spectrum rows
-        double* ob = reinterpret_cast<double*>(rb);
+        zw_last_pair<P, INV>(l, buf, va, vb);
+        if (ok) {
+            double* oa = reinterpret_cast<double*>(ra);      // in place: the real rows reuse the half-spectrum rows
+            double* ob = reinterpret_cast<double*>(rb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            oa[bA + j * P::M1] = va[j].x; ob[bA + j * P::M1] = va[j].y;
-            oa[bB + j * P::M1] = vb[j].x; ob[bB + j * P::M1] = vb[j].y;
+            for (int j = 0; j < 8; ++j) {
+                oa[bA + j * P::M1] = va[j].x; ob[bA + j * P::M1] = va[j].y;
+                oa[bB + j * P::M1] = vb[j].x; ob[bB + j * P::M1] = vb[j].y;
+            }
         }
         __syncwarp();
     }
-    (void)N;
 }
 
 template <class P>
 __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const ZArgs a) {
-    constexpr int WARPS = ZWarpPassCfg<P>::WARPS;
+    typedef ZWarpPassCfg<P> Cfg;
+    constexpr int LPT = Cfg::LPT, SUB = Cfg::SUB;
     extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
     const int wp = threadIdx.x >> 5, L = threadIdx.x & 31;
-    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + wp * P::NPAD;
+    const int l = L % LPT, sub = L / LPT;
+    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + (wp * SUB + sub) * P::NPAD;
     cplx* F = a.base + (long long)blockIdx.y * a.fstride;
     const cplx* __restrict__ tw = a.tw;
     const int kzout = a.kz_out;
     int bA, bB; bool self;
-    zw_lane_pair<P>(L, bA, bB, self);
+    zw_lane_pair<P>(l, bA, bB, self);
     cplx w1[7];
-    zw_load_tw1<P>(L, tw, w1);
-    const cplx w2a = tw[P::R1 * (L % P::M2)], w2b = tw[P::R1 * (L % P::M2) * 2], w2c = tw[P::R1 * (L % P::M2) * 4];   // see k_z_fused_w
-    for (long long pr = (long long)blockIdx.x * WARPS + wp; pr < a.npairs; pr += (long long)gridDim.x * WARPS) {
-        cplx* ra = F + 2 * pr * a.rs;
+    zw_load_tw1<P>(l, tw, w1);
+    const cplx w2a = tw[P::R1 * (l % P::M2)], w2b = tw[P::R1 * (l % P::M2) * 2], w2c = tw[P::R1 * (l % P::M2) * 4];   // see k_z_fused_w
+    for (long long p0 = ((long long)blockIdx.x * Cfg::WARPS + wp) * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * Cfg::PAIRS) {
+        const long long pr = p0 + sub;
+        const bool ok = pr < a.npairs;
+        cplx* ra = F + 2 * (ok ? pr : p0) * a.rs;
         cplx* rb = ra + a.rs;
         const double* ia = reinterpret_cast<const double*>(ra);
         const double* ib = reinterpret_cast<const double*>(rb);
@@ -897,13 +923,12 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const Z
         zw_bfly_pair<FWD>(self, ca, cb, w1);
         zw_scatter_pair<P>(bA, bB, buf, ca, cb);
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r8_base<P, FWD, 1>(L + 32 * i, buf, w2a, w2b, w2c);
+        zw_pass2<P, FWD>(l, buf, w2a, w2b, w2c);
         __syncwarp();
-        zw_last_pair<P, FWD>(L, buf, ca, cb);
+        zw_last_pair<P, FWD>(l, buf, ca, cb);
         __syncwarp();                                    // in place: every lane has read the real rows before the spectra overwrite them
-        zw_unpack_store<P>(L, ca, cb, [&](int k, cplx A, cplx B) {
-            if (k < kzout) { ra[k] = A; rb[k] = B; }
+        zw_unpack_store<P>(l, ca, cb, [&](int k, cplx A, cplx B) {
+            if (k < kzout && ok) { ra[k] = A; rb[k] = B; }
         });
         __syncwarp();
     }

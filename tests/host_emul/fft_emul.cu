@@ -399,6 +399,88 @@ template <class P> int check_fused_gen() {
     return err / nrm < 1e-13 ? 0 : 1;
 }
 
+// stand-alone warp z passes (k_z_c2r_w / k_z_r2c_w) with LPT = M1/2 lanes per transform: the lane program of one pencil
+// pair, lanes emulated one after the other between the __syncwarp points.  c2r against a long double DFT, then r2c of the
+// exact real rows against a long double DFT.
+template <class P> int check_warp_passes() {
+    typedef ZWarpPassCfg<P> Cfg;
+    constexpr int N = P::N, NP = P::NPAD, LPT = Cfg::LPT;
+    std::vector<cplx> tw(N), buf(NP, mk(1e300, 1e300));
+    for (int m = 0; m < N; ++m) {
+        long double a = -2.0L * 3.14159265358979323846264338327950288L * m / N;
+        tw[m] = mk((double)cosl(a), (double)sinl(a));
+    }
+    std::vector<cplx> rows[2];
+    for (int r = 0; r < 2; ++r) { rows[r].resize(N / 2 + 1); for (auto& z : rows[r]) z = mk(frand(), frand()); }
+    auto w2 = [&](int l, int j) { return tw[P::R1 * (l % P::M2) * j]; };
+    // ---- c2r
+    for (int l = 0; l < LPT; ++l) {
+        cplx w1[7]; zw_load_tw1<P>(l, tw.data(), w1);
+        zw_inv_pass1<P>(l, buf.data(), w1, [&](int k, cplx& A, cplx& B) { A = rows[0][k]; B = rows[1][k]; });
+    }
+    for (int l = 0; l < LPT; ++l) zw_pass2<P, INV>(l, buf.data(), w2(l, 1), w2(l, 2), w2(l, 4));
+    std::vector<double> got[2]; got[0].assign(N, 1e300); got[1].assign(N, 1e300);
+    for (int l = 0; l < LPT; ++l) {
+        int bA, bB; bool self; zw_lane_pair<P>(l, bA, bB, self);
+        cplx va[8], vb[8];
+        zw_last_pair<P, INV>(l, buf.data(), va, vb);
+        for (int j = 0; j < 8; ++j) {
+            got[0][bA + j * P::M1] = va[j].x; got[1][bA + j * P::M1] = va[j].y;
+            got[0][bB + j * P::M1] = vb[j].x; got[1][bB + j * P::M1] = vb[j].y;
+        }
+    }
+    std::vector<double> real[2];
+    double err = 0, nrm = 0;
+    for (int r = 0; r < 2; ++r) {
+        real[r].resize(N);
+        for (int n = 0; n < N; ++n) {
+            long double sacc = 0;
+            for (int k = 0; k < N; ++k) {
+                int kk = k <= N / 2 ? k : N - k;
+                long double ar = rows[r][kk].x, ai = (k <= N / 2 ? rows[r][kk].y : -rows[r][kk].y);
+                if (k == 0 || k == N / 2) ai = 0;
+                long double a = 2.0L * 3.14159265358979323846264338327950288L * ((long long)n * k % N) / N;
+                sacc += ar * cosl(a) - ai * sinl(a);
+            }
+            real[r][n] = (double)sacc;
+            err = fmax(err, fabs(got[r][n] - real[r][n])); nrm = fmax(nrm, fabs(real[r][n]));
+        }
+    }
+    // ---- r2c of the exact real rows
+    std::vector<cplx> outA(N / 2 + 1, mk(1e300, 1e300)), outB(N / 2 + 1, mk(1e300, 1e300));
+    std::vector<cplx> creg(LPT * 16);
+    for (int l = 0; l < LPT; ++l) {
+        int bA, bB; bool self; zw_lane_pair<P>(l, bA, bB, self);
+        cplx* ca = &creg[l * 16]; cplx* cb = ca + 8;
+        for (int j = 0; j < 8; ++j) { ca[j] = mk(real[0][bA + j * P::M1], real[1][bA + j * P::M1]); cb[j] = mk(real[0][bB + j * P::M1], real[1][bB + j * P::M1]); }
+        cplx w1[7]; zw_load_tw1<P>(l, tw.data(), w1);
+        zw_bfly_pair<FWD>(self, ca, cb, w1);
+    }
+    for (int l = 0; l < LPT; ++l) {
+        int bA, bB; bool self; zw_lane_pair<P>(l, bA, bB, self);
+        zw_scatter_pair<P>(bA, bB, buf.data(), &creg[l * 16], &creg[l * 16 + 8]);
+    }
+    for (int l = 0; l < LPT; ++l) zw_pass2<P, FWD>(l, buf.data(), w2(l, 1), w2(l, 2), w2(l, 4));
+    for (int l = 0; l < LPT; ++l) {
+        cplx va[8], vb[8];
+        zw_last_pair<P, FWD>(l, buf.data(), va, vb);
+        zw_unpack_store<P>(l, va, vb, [&](int k, cplx A, cplx B) { outA[k] = A; outB[k] = B; });
+    }
+    double err2 = 0, nrm2 = 0;
+    for (int r = 0; r < 2; ++r) for (int k = 0; k <= N / 2; ++k) {
+        long double sr = 0, si = 0;
+        for (int n = 0; n < N; ++n) {
+            long double a = -2.0L * 3.14159265358979323846264338327950288L * ((long long)n * k % N) / N;
+            sr += real[r][n] * cosl(a); si += real[r][n] * sinl(a);
+        }
+        cplx g = r == 0 ? outA[k] : outB[k];
+        err2 = fmax(err2, fmax(fabs(g.x - (double)sr), fabs(g.y - (double)si)));
+        nrm2 = fmax(nrm2, fmax(fabs((double)sr), fabs((double)si)));
+    }
+    printf("warp z passes N=%d (%d,%d,%d), %d lanes per transform: c2r max rel err %.3e, r2c %.3e\n", N, P::R1, P::R2, P::R3, LPT, err / nrm, err2 / nrm2);
+    return (err / nrm < 1e-13 && err2 / nrm2 < 1e-13) ? 0 : 1;
+}
+
 int main() {
     int bad = 0;
     bad += check<BigPlan<16>::type>("big");
@@ -427,6 +509,9 @@ int main() {
     bad += check_fused<FftPlan<256, 4, 4, 4, 1, 4>>();
     bad += check_fused<ZFPlan<1024>::type>();
     bad += check_fused_warp<ZFPlan<512>::type>();
+    bad += check_warp_passes<ZWPlan<512>::type>();
+    bad += check_warp_passes<ZWPlan<256>::type>();
+    bad += check_warp_passes<ZWPlan<128>::type>();
     bad += check_fused_gen<FftPlan<512, 8, 8, 8>>();
     bad += check_fused_gen<FftPlan<1024, 8, 16, 8>>();
     bad += check_pack<16>();

@@ -92,6 +92,16 @@ def test_strided_and_fused_z_kernel_generations_agree_to_rounding():
         assert abs(e - e0) <= 1e-13 * abs(e0)
 
 
+@pytest.mark.parametrize("n", [128, 256])
+def test_sub_warp_z_passes_agree_with_the_first_generation(n):
+    """128^3 / 256^3: the stand-alone z passes run 4 / 2 pencil pairs side by side in a warp (plans 8 x 2 x 8, 8 x 4 x 8); the
+    random-phase initial condition goes through them (c2r + r2c round trip).  Against the first-generation kernels
+    (NSB200_ZF=old): energies after two steps to 1e-13.  (Fields against pocketfft: tests/test_gpu_parity.py.)"""
+    _, e0 = run_variant(n, {})
+    _, e1 = run_variant(n, {"NSB200_ZF": "old"})
+    assert abs(e1 - e0) <= 1e-13 * abs(e0)
+
+
 def test_1024_general_warp_kernels_agree_with_the_first_generation():
     """1024^3: z kernels in the general warp-per-transform form (two mirrored pairs per lane, radix-16 middle pass, twiddle
     powers formed on the fly) against the first-generation kernels (4-pass plan, table twiddles): two steps, energy to 1e-13.
