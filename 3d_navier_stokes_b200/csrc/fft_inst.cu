@@ -12,17 +12,13 @@
 #define NSB_CAT(a, b) NSB_CAT2(a, b)
 #define NSB_FN(name) NSB_CAT(name, NSB_N)
 
-// the warp-per-transform fused z kernel exists for the 8 x 8 x 8 plan (64 butterflies per pass)
-#if NSB_N == 512
-#define NSB_HAVE_ZFW 1
-#else
-#define NSB_HAVE_ZFW 0
-#endif
-// the stand-alone warp-per-pair z passes also exist for 256 = 8 x 4 x 8 and 128 = 8 x 2 x 8 (two / four pencil pairs side by
-// side in a warp)
+// the warp-per-transform z kernels (fused and stand-alone) exist for the plans 8 x R2 x 8 with 64, 32 or 16 butterflies per
+// pass: 512 = 8 x 8 x 8, 256 = 8 x 4 x 8 and 128 = 8 x 2 x 8 (two / four pencil pairs side by side in a warp)
 #if NSB_N == 512 || NSB_N == 256 || NSB_N == 128
+#define NSB_HAVE_ZFW 1
 #define NSB_HAVE_ZPW 1
 #else
+#define NSB_HAVE_ZFW 0
 #define NSB_HAVE_ZPW 0
 #endif
 // ... and in its general form (two mirrored pairs per lane, radix-16 middle pass) for 1024 = 8 x 16 x 8
@@ -67,7 +63,7 @@ int setup() {
     if (e != cudaSuccess) return (int)e;
 #if NSB_HAVE_ZFW
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_z_fused_w<ZF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpCfg<ZF>::SMEM);
+    e = cudaFuncSetAttribute(k_z_fused_w<ZW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpCfg<ZW>::SMEM);
 #endif
 #if NSB_HAVE_ZPW
     if (e != cudaSuccess) return (int)e;
@@ -203,7 +199,7 @@ int zlaunch(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s) 
     if (which == NSB_Z_C2R) k_z_c2r<ZP><<<dim3(grid_x, nfields), TH, kZSmem, s>>>(*a);
     else if (which == NSB_Z_R2C) k_z_r2c<ZP><<<dim3(grid_x, nfields), TH, kZSmem, s>>>(*a);
 #if NSB_HAVE_ZFW
-    else if (which == NSB_Z_FUSED_W) k_z_fused_w<ZF><<<dim3(grid_x), ZWarpCfg<ZF>::THREADS, ZWarpCfg<ZF>::SMEM, s>>>(*a);
+    else if (which == NSB_Z_FUSED_W) k_z_fused_w<ZW><<<dim3(grid_x), ZWarpCfg<ZW>::THREADS, ZWarpCfg<ZW>::SMEM, s>>>(*a);
 #endif
 #if NSB_HAVE_ZPW
     else if (which == NSB_Z_C2R_W) k_z_c2r_w<ZW><<<dim3(grid_x, nfields), ZWarpPassCfg<ZW>::THREADS, ZWarpPassCfg<ZW>::SMEM, s>>>(*a);
@@ -224,7 +220,7 @@ int zocc(int which) {
     if (which == NSB_Z_C2R) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_c2r<ZP>, TH, kZSmem);
     else if (which == NSB_Z_R2C) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_r2c<ZP>, TH, kZSmem);
 #if NSB_HAVE_ZFW
-    else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused_w<ZF>, ZWarpCfg<ZF>::THREADS, ZWarpCfg<ZF>::SMEM);
+    else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused_w<ZW>, ZWarpCfg<ZW>::THREADS, ZWarpCfg<ZW>::SMEM);
 #endif
 #if NSB_HAVE_ZPW
     else if (which == NSB_Z_C2R_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_c2r_w<ZW>, ZWarpPassCfg<ZW>::THREADS, ZWarpPassCfg<ZW>::SMEM);
@@ -240,15 +236,18 @@ int zocc(int which) {
 }
 }  // namespace
 
-// pencil pairs per CTA of the stand-alone warp passes (0: not built for this N)
+// pencil pairs per CTA of the warp kernels (0: not built for this N; < 0: built but not the default)
 #if NSB_HAVE_ZPW
+#define NSB_ZFW_PAIRS ZWarpCfg<ZW>::SUB
 #define NSB_ZPW_PAIRS ZWarpPassCfg<ZW>::PAIRS
 #elif NSB_HAVE_ZG
+#define NSB_ZFW_PAIRS (-1)
 #define NSB_ZPW_PAIRS 4
 #else
+#define NSB_ZFW_PAIRS 0
 #define NSB_ZPW_PAIRS 0
 #endif
 extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, NSB_PIPE_TCOLS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G,
      // 1024: the general fused kernel (249 registers, 2 x 3 warps per SM) measured slower than the first generation (117.5 vs 108.8 ms
      // per step), the stand-alone passes faster (65 vs 56 % of the HBM peak): NSB200_ZF=warp still selects it for experiments
-     NSB_HAVE_ZFW ? 1 : (NSB_HAVE_ZG ? -1 : 0), NSB_ZPW_PAIRS, NSB_ZPW_PAIRS}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC, NSB_RING_FN, NSB_LINK_FN};
+     NSB_ZFW_PAIRS, NSB_ZPW_PAIRS, NSB_ZPW_PAIRS}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC, NSB_RING_FN, NSB_LINK_FN};

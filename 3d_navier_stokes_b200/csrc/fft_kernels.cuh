@@ -627,10 +627,12 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
 // Warp t inverse-transforms u_{t+1} and w_{t+2}, forms component t of u x w at its own points and transforms it
 // forward in the buffer of u_{t+1}.
 template <class P> struct ZWarpCfg {
-    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && P::M1 == 64, "warp-per-transform kernel: plan 8 x R2 x 8 with 64 butterflies per pass");
-    static_assert(P::NB2 % 32 == 0 && 32 % P::M2 == 0 && P::R2 == 8, "pass 2 must split evenly over the warp with one twiddle set per lane");
+    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && (P::M1 == 64 || P::M1 == 32 || P::M1 == 16) && P::M2 == 8,
+                  "warp-per-transform kernel: plan 8 x R2 x 8 with 64, 32 or 16 butterflies per pass");
+    static constexpr int LPT = P::M1 / 2;             // lanes per transform: lane l owns the mirrored pair (l, M1 - l)
+    static constexpr int SUB = 32 / LPT;              // pencil pairs side by side in the CTA (N = 256: 2, N = 128: 4)
     static constexpr int THREADS = 96;
-    static constexpr int SMEM = 6 * P::NPAD * 16;
+    static constexpr int SMEM = SUB * 6 * P::NPAD * 16;
 #ifndef NSB_ZFW_MINB
 #define NSB_ZFW_MINB 4
 #endif
@@ -745,36 +747,64 @@ template <class P, class St> NSB_HD void zw_unpack_store(int L, const cplx* va, 
     }
 }
 
+// middle pass by the LPT lanes of a transform: NB2 / LPT butterflies per lane, all with the lane's m2 = l % 8
+template <class P, int DIR> NSB_HD void zw_pass2(int l, cplx* buf, cplx w2a, cplx w2b, cplx w2c) {
+    constexpr int LPT = P::M1 / 2;
+#pragma unroll
+    for (int i = 0; i < P::NB2 / LPT; ++i) {
+        if constexpr (P::R2 == 8) fft_pass2_r8_base<P, DIR, 1>(l + LPT * i, buf, w2a, w2b, w2c);
+        else if constexpr (P::R2 == 4) fft_pass2_r4_base<P, DIR, 1>(l + LPT * i, buf, w2a, w2b);
+        else fft_pass2_r2_base<P, DIR, 1>(l + LPT * i, buf, w2a);
+    }
+}
+
 template <class P>
 __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_fused_w(const ZArgs a) {
-    constexpr int NP = P::NPAD;
+    typedef ZWarpCfg<P> Cfg;
+    constexpr int NP = P::NPAD, LPT = Cfg::LPT, SUB = Cfg::SUB;
     extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
-    cplx* sm = reinterpret_cast<cplx*>(nsb_smem_raw);
     const int t = threadIdx.x >> 5;          // warp = output component
     const int L = threadIdx.x & 31;
+    const int l = L % LPT, sub = L / LPT;    // lane of the transform, pencil pair of the CTA trip (SUB = 1 for N = 512)
+    cplx* sm = reinterpret_cast<cplx*>(nsb_smem_raw) + sub * 6 * NP;
     const cplx* __restrict__ tw = a.tw;
     const int kzin = a.kz_in, kzout = a.kz_out;
     const int i1 = (t + 1) % 3, i2 = (t + 2) % 3;
     const int fu = i1, fw = 3 + i2;          // the two fields this warp brings to real space
     int bA, bB; bool self;
-    zw_lane_pair<P>(L, bA, bB, self);
+    zw_lane_pair<P>(l, bA, bB, self);
     const int rbA = fft_row_base<P>(bA), rbB = fft_row_base<P>(bB);
     cplx w1[7];
-    zw_load_tw1<P>(L, tw, w1);
-    // pass-2 twiddles W^{8 (L % 8) kp}: powers 1, 2, 4 in registers, the others formed on the fly (the kernel is bound by the
+    zw_load_tw1<P>(l, tw, w1);
+    // pass-2 twiddles W^{8 (l % 8) kp}: powers 1, 2, 4 in registers, the others formed on the fly (the kernel is bound by the
     // shared-memory pipe, not by FP64, and the 16 registers saved end the spilling at 4 CTAs per SM)
-    const cplx w2a = tw[P::R1 * (L % P::M2)], w2b = tw[P::R1 * (L % P::M2) * 2], w2c = tw[P::R1 * (L % P::M2) * 4];
-    for (long long pr = blockIdx.x; pr < a.npairs; pr += gridDim.x) {
-        const long long roff = 2 * pr * a.rs;
+    const cplx w2a = tw[P::R1 * (l % P::M2)], w2b = tw[P::R1 * (l % P::M2) * 2], w2c = tw[P::R1 * (l % P::M2) * 4];
+    for (long long p0 = (long long)blockIdx.x * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * SUB) {
+        const long long pr = p0 + sub;
+        const bool ok = pr < a.npairs;                     // the last trip may hold fewer than SUB pairs
+        const long long roff = 2 * (ok ? pr : p0) * a.rs;
 #if defined(__CUDA_ARCH__) && !defined(NSB_ZFW_NO_PREFETCH)
-        // pull the next pair of this CTA into L2 while this one is transformed (12 rows of kz_in entries)
-        if (pr + gridDim.x < a.npairs) {
-            const long long nroff = 2 * (pr + gridDim.x) * a.rs;
+        // pull the next pair(s) of this CTA into L2 while these are transformed (12 rows of kz_in entries each)
+        if constexpr (SUB == 1) {
+            if (pr + gridDim.x < a.npairs) {
+                const long long nroff = 2 * (pr + gridDim.x) * a.rs;
+                const int lines = (kzin * 16 + 127) / 128;
+                for (int i = threadIdx.x; i < 12 * lines; i += 96) {
+                    const int row = i / lines, ln = i % lines;
+                    const cplx* p = a.base + (row >> 1) * a.fstride + nroff + (row & 1) * a.rs + ln * 8;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
+            }
+        } else {
             const int lines = (kzin * 16 + 127) / 128;
-            for (int i = threadIdx.x; i < 12 * lines; i += 96) {
-                const int row = i / lines, ln = i % lines;
-                const cplx* p = a.base + (row >> 1) * a.fstride + nroff + (row & 1) * a.rs + ln * 8;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            for (int i = threadIdx.x; i < SUB * 12 * lines; i += 96) {
+                const int s2 = i / (12 * lines), r2 = i % (12 * lines);
+                const long long npr = p0 + (long long)gridDim.x * SUB + s2;
+                if (npr < a.npairs) {
+                    const int row = r2 / lines, ln = r2 % lines;
+                    const cplx* p = a.base + (row >> 1) * a.fstride + 2 * npr * a.rs + (row & 1) * a.rs + ln * 8;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
             }
         }
 #endif
@@ -785,15 +815,14 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
             cplx* buf = sm + f * NP;
             const cplx* ra = a.base + f * a.fstride + roff;
             const cplx* rb = ra + a.rs;
-            zw_inv_pass1<P>(L, buf, w1, [&](int k, cplx& A, cplx& B) {
-                if (k < kzin) { A = NSB_LDCG(ra + k); B = NSB_LDCG(rb + k); }
+            zw_inv_pass1<P>(l, buf, w1, [&](int k, cplx& A, cplx& B) {
+                if (k < kzin && ok) { A = NSB_LDCG(ra + k); B = NSB_LDCG(rb + k); }
                 else { A = mk(0.0, 0.0); B = mk(0.0, 0.0); }
             });
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r8_base<P, INV, 1>(L + 32 * i, buf, w2a, w2b, w2c);
+            zw_pass2<P, INV>(l, buf, w2a, w2b, w2c);
             __syncwarp();
-            zw_last_pair<P, INV>(L, buf, ca, cb);
+            zw_last_pair<P, INV>(l, buf, ca, cb);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { buf[rbA + j] = ca[j]; buf[rbB + j] = cb[j]; }   // in place (the lane's own rows): point bA + j M1 lives at rbA + j
         }
@@ -813,14 +842,13 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
         cplx* buf = sm + fu * NP;
         zw_scatter_pair<P>(bA, bB, buf, ca, cb);
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r8_base<P, FWD, 1>(L + 32 * i, buf, w2a, w2b, w2c);
+        zw_pass2<P, FWD>(l, buf, w2a, w2b, w2c);
         __syncwarp();
-        zw_last_pair<P, FWD>(L, buf, ca, cb);
+        zw_last_pair<P, FWD>(l, buf, ca, cb);
         cplx* oa = a.base + t * a.fstride + roff;
         cplx* ob = oa + a.rs;
-        zw_unpack_store<P>(L, ca, cb, [&](int k, cplx A, cplx B) {
-            if (k < kzout) { oa[k] = A; ob[k] = B; }
+        zw_unpack_store<P>(l, ca, cb, [&](int k, cplx A, cplx B) {
+            if (k < kzout && ok) { oa[k] = A; ob[k] = B; }
         });
         __syncwarp();                                      // the buffer is free for the next pair's inverse pass 1
     }
@@ -837,17 +865,6 @@ template <class P> struct ZWarpPassCfg {
     static constexpr int SUB = 32 / LPT;              // transforms side by side in a warp
     static constexpr int WARPS = 4, THREADS = 32 * WARPS, PAIRS = WARPS * SUB, SMEM = PAIRS * P::NPAD * 16;
 };
-// middle pass by the LPT lanes of a transform: NB2 / LPT butterflies per lane, all with the lane's m2 = l % 8
-template <class P, int DIR> NSB_HD void zw_pass2(int l, cplx* buf, cplx w2a, cplx w2b, cplx w2c) {
-    constexpr int LPT = ZWarpPassCfg<P>::LPT;
-#pragma unroll
-    for (int i = 0; i < P::NB2 / LPT; ++i) {
-        if constexpr (P::R2 == 8) fft_pass2_r8_base<P, DIR, 1>(l + LPT * i, buf, w2a, w2b, w2c);
-        else if constexpr (P::R2 == 4) fft_pass2_r4_base<P, DIR, 1>(l + LPT * i, buf, w2a, w2b);
-        else fft_pass2_r2_base<P, DIR, 1>(l + LPT * i, buf, w2a);
-    }
-}
-
 template <class P>
 __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const ZArgs a) {
     typedef ZWarpPassCfg<P> Cfg;
