@@ -21,7 +21,8 @@
 #define NSB_HAVE_ZFW 0
 #define NSB_HAVE_ZPW 0
 #endif
-// ... and in its general form (two mirrored pairs per lane, radix-16 middle pass) for 1024 = 8 x 16 x 8
+// 1024 = 8 x 16 x 8: the fused kernel with two warps per transform, the stand-alone passes in the general one-warp form (two
+// mirrored pairs per lane, radix-16 middle pass)
 #if NSB_N == 1024
 #define NSB_HAVE_ZG 1
 #else
@@ -73,7 +74,7 @@ int setup() {
 #endif
 #if NSB_HAVE_ZG
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_zg_fused<ZG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZGenCfg<ZG>::FUSED_SMEM);
+    e = cudaFuncSetAttribute(k_z_fused_w<ZG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpCfg<ZG>::SMEM);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_zg_c2r<ZG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZGenCfg<ZG>::PASS_SMEM);
     if (e != cudaSuccess) return (int)e;
@@ -206,7 +207,7 @@ int zlaunch(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s) 
     else if (which == NSB_Z_R2C_W) k_z_r2c_w<ZW><<<dim3(grid_x, nfields), ZWarpPassCfg<ZW>::THREADS, ZWarpPassCfg<ZW>::SMEM, s>>>(*a);
 #endif
 #if NSB_HAVE_ZG
-    else if (which == NSB_Z_FUSED_W) k_zg_fused<ZG><<<dim3(grid_x), ZGenCfg<ZG>::FUSED_THREADS, ZGenCfg<ZG>::FUSED_SMEM, s>>>(*a);
+    else if (which == NSB_Z_FUSED_W) k_z_fused_w<ZG><<<dim3(grid_x), ZWarpCfg<ZG>::THREADS, ZWarpCfg<ZG>::SMEM, s>>>(*a);
     else if (which == NSB_Z_C2R_W) k_zg_c2r<ZG><<<dim3(grid_x, nfields), ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM, s>>>(*a);
     else if (which == NSB_Z_R2C_W) k_zg_r2c<ZG><<<dim3(grid_x, nfields), ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM, s>>>(*a);
 #endif
@@ -227,7 +228,7 @@ int zocc(int which) {
     else if (which == NSB_Z_R2C_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_r2c_w<ZW>, ZWarpPassCfg<ZW>::THREADS, ZWarpPassCfg<ZW>::SMEM);
 #endif
 #if NSB_HAVE_ZG
-    else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zg_fused<ZG>, ZGenCfg<ZG>::FUSED_THREADS, ZGenCfg<ZG>::FUSED_SMEM);
+    else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused_w<ZG>, ZWarpCfg<ZG>::THREADS, ZWarpCfg<ZG>::SMEM);
     else if (which == NSB_Z_C2R_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zg_c2r<ZG>, ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM);
     else if (which == NSB_Z_R2C_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zg_r2c<ZG>, ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM);
 #endif
@@ -241,13 +242,13 @@ int zocc(int which) {
 #define NSB_ZFW_PAIRS ZWarpCfg<ZW>::SUB
 #define NSB_ZPW_PAIRS ZWarpPassCfg<ZW>::PAIRS
 #elif NSB_HAVE_ZG
-#define NSB_ZFW_PAIRS (-1)
+#define NSB_ZFW_PAIRS 1
 #define NSB_ZPW_PAIRS 4
 #else
 #define NSB_ZFW_PAIRS 0
 #define NSB_ZPW_PAIRS 0
 #endif
 extern const FftOps NSB_FN(nsb_fft_ops_) = {NSB_N, ST, TmaChunk<NSB_N>::ROWS, NSB_PIPE_TCOLS, {ZCfg<ZP>::G, ZCfg<ZP>::G, ZFusedCfg<ZF>::G,
-     // 1024: the general fused kernel (249 registers, 2 x 3 warps per SM) measured slower than the first generation (117.5 vs 108.8 ms
-     // per step), the stand-alone passes faster (65 vs 56 % of the HBM peak): NSB200_ZF=warp still selects it for experiments
+     // 1024: the fused kernel runs two warps per transform (one mirrored pair per lane, 168 registers, 2 x 6 warps per SM:
+     // 82.5 ms per step against 108.1 ms for the first generation and 117.5 ms for one warp with two pairs per lane)
      NSB_ZFW_PAIRS, NSB_ZPW_PAIRS, NSB_ZPW_PAIRS}, setup, strided, zlaunch, zocc, NSB_PIPE_FN, NSB_PIPE_OCC, NSB_RING_FN, NSB_LINK_FN};

@@ -13,8 +13,10 @@
 //   k_z_fused       z c2r of (u, w) -> u x w -> z r2c in one kernel: the six real-space fields of a
 //                   pencil pair never leave the SM (reference loops solver.c:664-677 between the
 //                   transforms of :656/:658 and :683).
-//   k_z_fused_w, k_z_c2r_w, k_z_r2c_w (N = 512), k_zg_* (general form, N = 1024)  the same z kernels with ONE WARP per
-//                   transform and Hermitian-mirrored butterfly pairs per lane (second generation).
+//   k_z_fused_w, k_z_c2r_w, k_z_r2c_w  the same z kernels with Hermitian-mirrored butterfly pairs per lane and warp-level
+//                   synchronisation (second generation): one warp per transform at N = 512, two / four transforms side by
+//                   side in a warp at 256 / 128, two warps per transform (named barrier) for the fused kernel at 1024;
+//                   k_zg_c2r, k_zg_r2c: the stand-alone passes at 1024 (one warp, two mirrored pairs per lane).
 #pragma once
 #include <cuda.h>
 #include "fft_core.cuh"
@@ -627,16 +629,35 @@ __global__ void __launch_bounds__(ZFusedCfg<P>::THREADS, ZFusedCfg<P>::MINB) k_z
 // Warp t inverse-transforms u_{t+1} and w_{t+2}, forms component t of u x w at its own points and transforms it
 // forward in the buffer of u_{t+1}.
 template <class P> struct ZWarpCfg {
-    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && (P::M1 == 64 || P::M1 == 32 || P::M1 == 16) && P::M2 == 8,
-                  "warp-per-transform kernel: plan 8 x R2 x 8 with 64, 32 or 16 butterflies per pass");
-    static constexpr int LPT = P::M1 / 2;             // lanes per transform: lane l owns the mirrored pair (l, M1 - l)
-    static constexpr int SUB = 32 / LPT;              // pencil pairs side by side in the CTA (N = 256: 2, N = 128: 4)
-    static constexpr int THREADS = 96;
+    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && (P::M1 == 128 || P::M1 == 64 || P::M1 == 32 || P::M1 == 16) && P::M2 == 8,
+                  "warp-per-transform kernel: plan 8 x R2 x 8 with 128, 64, 32 or 16 butterflies per pass");
+    static constexpr int LPT = P::M1 / 2;                       // lanes per transform: lane l owns the mirrored pair (l, M1 - l)
+    static constexpr int WPT = LPT > 32 ? LPT / 32 : 1;         // warps per transform (N = 1024: 2, synchronised by a named barrier)
+    static constexpr int SUB = LPT < 32 ? 32 / LPT : 1;         // pencil pairs side by side in the CTA (N = 256: 2, N = 128: 4)
+    static constexpr int THREADS = 96 * WPT;
     static constexpr int SMEM = SUB * 6 * P::NPAD * 16;
 #ifndef NSB_ZFW_MINB
 #define NSB_ZFW_MINB 4
 #endif
-    static constexpr int MINB = NSB_ZFW_MINB;
+    static constexpr int MINB = WPT > 1 ? 2 : NSB_ZFW_MINB;
+};
+// the lanes of one transform meet between its passes: one warp -> __syncwarp, two warps -> named barrier 1 + transform index
+template <int WPT> __device__ __forceinline__ void zw_tsync(int t) {
+#ifdef __CUDA_ARCH__
+    if constexpr (WPT == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "n"(32 * WPT) : "memory");
+#else
+    (void)t;
+#endif
+}
+// pass-2 twiddle bases of a lane: W^{8 m2 kp} for kp = 1, 2, 4 (, 8): the other powers are formed on the fly
+template <class P> struct ZwTw2 {
+    cplx a, b, c, d;
+    NSB_HD ZwTw2(int l, const cplx* __restrict__ tw) {
+        const int t = P::R1 * (l % P::M2);
+        a = tw[t]; b = tw[2 * t]; c = tw[4 * t];
+        if constexpr (P::R2 == 16) d = tw[8 * t]; else d = mk(1.0, 0.0);
+    }
 };
 
 NSB_HD cplx zw_pack(cplx A, cplx B) { return mk(A.x - B.y, A.y + B.x); }     // element n <= N/2 : A + i B
@@ -748,24 +769,24 @@ template <class P, class St> NSB_HD void zw_unpack_store(int L, const cplx* va, 
 }
 
 // middle pass by the LPT lanes of a transform: NB2 / LPT butterflies per lane, all with the lane's m2 = l % 8
-template <class P, int DIR> NSB_HD void zw_pass2(int l, cplx* buf, cplx w2a, cplx w2b, cplx w2c) {
+template <class P, int DIR> NSB_HD void zw_pass2(int l, cplx* buf, const ZwTw2<P>& w) {
     constexpr int LPT = P::M1 / 2;
 #pragma unroll
     for (int i = 0; i < P::NB2 / LPT; ++i) {
-        if constexpr (P::R2 == 8) fft_pass2_r8_base<P, DIR, 1>(l + LPT * i, buf, w2a, w2b, w2c);
-        else if constexpr (P::R2 == 4) fft_pass2_r4_base<P, DIR, 1>(l + LPT * i, buf, w2a, w2b);
-        else fft_pass2_r2_base<P, DIR, 1>(l + LPT * i, buf, w2a);
+        if constexpr (P::R2 == 16) fft_pass2_r16_base<P, DIR, 1>(l + LPT * i, buf, w.a, w.b, w.c, w.d);
+        else if constexpr (P::R2 == 8) fft_pass2_r8_base<P, DIR, 1>(l + LPT * i, buf, w.a, w.b, w.c);
+        else if constexpr (P::R2 == 4) fft_pass2_r4_base<P, DIR, 1>(l + LPT * i, buf, w.a, w.b);
+        else fft_pass2_r2_base<P, DIR, 1>(l + LPT * i, buf, w.a);
     }
 }
-
 template <class P>
 __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_fused_w(const ZArgs a) {
     typedef ZWarpCfg<P> Cfg;
-    constexpr int NP = P::NPAD, LPT = Cfg::LPT, SUB = Cfg::SUB;
+    constexpr int NP = P::NPAD, LPT = Cfg::LPT, SUB = Cfg::SUB, WPT = Cfg::WPT, TPT = 32 * WPT;
     extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
-    const int t = threadIdx.x >> 5;          // warp = output component
-    const int L = threadIdx.x & 31;
-    const int l = L % LPT, sub = L / LPT;    // lane of the transform, pencil pair of the CTA trip (SUB = 1 for N = 512)
+    const int t = threadIdx.x / TPT;         // warp (or warp pair) = output component
+    const int L = threadIdx.x % TPT;
+    const int l = L % LPT, sub = L / LPT;    // lane of the transform, pencil pair of the CTA trip (SUB = 1 for N >= 512)
     cplx* sm = reinterpret_cast<cplx*>(nsb_smem_raw) + sub * 6 * NP;
     const cplx* __restrict__ tw = a.tw;
     const int kzin = a.kz_in, kzout = a.kz_out;
@@ -776,9 +797,9 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
     const int rbA = fft_row_base<P>(bA), rbB = fft_row_base<P>(bB);
     cplx w1[7];
     zw_load_tw1<P>(l, tw, w1);
-    // pass-2 twiddles W^{8 (l % 8) kp}: powers 1, 2, 4 in registers, the others formed on the fly (the kernel is bound by the
-    // shared-memory pipe, not by FP64, and the 16 registers saved end the spilling at 4 CTAs per SM)
-    const cplx w2a = tw[P::R1 * (l % P::M2)], w2b = tw[P::R1 * (l % P::M2) * 2], w2c = tw[P::R1 * (l % P::M2) * 4];
+    // pass-2 twiddles W^{8 (l % 8) kp}: powers 1, 2, 4 (, 8) in registers, the others formed on the fly (the kernel is bound by
+    // the shared-memory pipe, not by FP64, and the 16 registers saved end the spilling at 4 CTAs per SM)
+    const ZwTw2<P> w2(l, tw);
     for (long long p0 = (long long)blockIdx.x * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * SUB) {
         const long long pr = p0 + sub;
         const bool ok = pr < a.npairs;                     // the last trip may hold fewer than SUB pairs
@@ -789,7 +810,7 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
             if (pr + gridDim.x < a.npairs) {
                 const long long nroff = 2 * (pr + gridDim.x) * a.rs;
                 const int lines = (kzin * 16 + 127) / 128;
-                for (int i = threadIdx.x; i < 12 * lines; i += 96) {
+                for (int i = threadIdx.x; i < 12 * lines; i += Cfg::THREADS) {
                     const int row = i / lines, ln = i % lines;
                     const cplx* p = a.base + (row >> 1) * a.fstride + nroff + (row & 1) * a.rs + ln * 8;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -797,7 +818,7 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
             }
         } else {
             const int lines = (kzin * 16 + 127) / 128;
-            for (int i = threadIdx.x; i < SUB * 12 * lines; i += 96) {
+            for (int i = threadIdx.x; i < SUB * 12 * lines; i += Cfg::THREADS) {
                 const int s2 = i / (12 * lines), r2 = i % (12 * lines);
                 const long long npr = p0 + (long long)gridDim.x * SUB + s2;
                 if (npr < a.npairs) {
@@ -819,9 +840,9 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
                 if (k < kzin && ok) { A = NSB_LDCG(ra + k); B = NSB_LDCG(rb + k); }
                 else { A = mk(0.0, 0.0); B = mk(0.0, 0.0); }
             });
-            __syncwarp();
-            zw_pass2<P, INV>(l, buf, w2a, w2b, w2c);
-            __syncwarp();
+            zw_tsync<WPT>(t);
+            zw_pass2<P, INV>(l, buf, w2);
+            zw_tsync<WPT>(t);
             zw_last_pair<P, INV>(l, buf, ca, cb);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { buf[rbA + j] = ca[j]; buf[rbB + j] = cb[j]; }   // in place (the lane's own rows): point bA + j M1 lives at rbA + j
@@ -841,16 +862,16 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
         __syncthreads();                                   // all reads of the real-space fields are done
         cplx* buf = sm + fu * NP;
         zw_scatter_pair<P>(bA, bB, buf, ca, cb);
-        __syncwarp();
-        zw_pass2<P, FWD>(l, buf, w2a, w2b, w2c);
-        __syncwarp();
+        zw_tsync<WPT>(t);
+        zw_pass2<P, FWD>(l, buf, w2);
+        zw_tsync<WPT>(t);
         zw_last_pair<P, FWD>(l, buf, ca, cb);
         cplx* oa = a.base + t * a.fstride + roff;
         cplx* ob = oa + a.rs;
         zw_unpack_store<P>(l, ca, cb, [&](int k, cplx A, cplx B) {
             if (k < kzout && ok) { oa[k] = A; ob[k] = B; }
         });
-        __syncwarp();                                      // the buffer is free for the next pair's inverse pass 1
+        zw_tsync<WPT>(t);                                      // the buffer is free for the next pair's inverse pass 1
     }
 }
 
@@ -880,7 +901,7 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const Z
     zw_lane_pair<P>(l, bA, bB, self);
     cplx w1[7];
     zw_load_tw1<P>(l, tw, w1);
-    const cplx w2a = tw[P::R1 * (l % P::M2)], w2b = tw[P::R1 * (l % P::M2) * 2], w2c = tw[P::R1 * (l % P::M2) * 4];   // see k_z_fused_w
+    const ZwTw2<P> w2(l, tw);                          // see k_z_fused_w
     for (long long p0 = ((long long)blockIdx.x * Cfg::WARPS + wp) * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * Cfg::PAIRS) {
         const long long pr = p0 + sub;
         const bool ok = pr < a.npairs;                   // the last warp trip may hold fewer than SUB pairs
@@ -891,7 +912,7 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const Z
             else { A = mk(0.0, 0.0); B = mk(0.0, 0.0); }
         });
         __syncwarp();
-        zw_pass2<P, INV>(l, buf, w2a, w2b, w2c);
+        zw_pass2<P, INV>(l, buf, w2);
         __syncwarp();
         cplx va[8], vb[8];
         zw_last_pair<P, INV>(l, buf, va, vb);
@@ -923,7 +944,7 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const Z
     zw_lane_pair<P>(l, bA, bB, self);
     cplx w1[7];
     zw_load_tw1<P>(l, tw, w1);
-    const cplx w2a = tw[P::R1 * (l % P::M2)], w2b = tw[P::R1 * (l % P::M2) * 2], w2c = tw[P::R1 * (l % P::M2) * 4];   // see k_z_fused_w
+    const ZwTw2<P> w2(l, tw);                          // see k_z_fused_w
     for (long long p0 = ((long long)blockIdx.x * Cfg::WARPS + wp) * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * Cfg::PAIRS) {
         const long long pr = p0 + sub;
         const bool ok = pr < a.npairs;
@@ -940,7 +961,7 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const Z
         zw_bfly_pair<FWD>(self, ca, cb, w1);
         zw_scatter_pair<P>(bA, bB, buf, ca, cb);
         __syncwarp();
-        zw_pass2<P, FWD>(l, buf, w2a, w2b, w2c);
+        zw_pass2<P, FWD>(l, buf, w2);
         __syncwarp();
         zw_last_pair<P, FWD>(l, buf, ca, cb);
         __syncwarp();                                    // in place: every lane has read the real rows before the spectra overwrite them
@@ -951,16 +972,15 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const Z
     }
 }
 
-// ------------------------------------------------------------------------------ warp-per-transform z kernels, general form
-// The same construction for plans 8 x R2 x 8 with M1 = N/8 = 64 * NPR butterflies per pass (N = 1024: 8 x 16 x 8, two
-// mirrored pairs per lane, radix-16 middle pass).  All twiddles are formed on the fly from the powers 1, 2, 4 (, 8) of the
+// ------------------------------------------------------------------------------ warp-per-pair z passes, general form
+// The stand-alone passes for plans 8 x R2 x 8 with M1 = N/8 = 64 * NPR butterflies per pass (N = 1024: 8 x 16 x 8, two
+// mirrored pairs per lane, radix-16 middle pass; the fused kernel at 1024 is k_z_fused_w with two warps per transform).  All twiddles are formed on the fly from the powers 1, 2, 4 (, 8) of the
 // butterfly's base twiddle, so the register file has room for the second pair.  Pair i of lane L: i = 0 is (L, M1 - L)
 // (lane 0: the self-mirrored butterflies 0 and M1/2), i >= 1 is (32 i + L, M1 - 32 i - L).
 template <class P> struct ZGenCfg {
     static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && P::M1 % 64 == 0 && P::M2 == 8 && (P::R2 == 8 || P::R2 == 16),
                   "general warp-per-transform kernels: plan 8 x (8 | 16) x 8");
     static constexpr int NPR = P::M1 / 64;
-    static constexpr int FUSED_THREADS = 96, FUSED_SMEM = 6 * P::NPAD * 16;
     static constexpr int WARPS = 4, PASS_THREADS = 32 * WARPS, PASS_SMEM = WARPS * P::NPAD * 16;
 };
 template <class P> NSB_HD void zg_pair(int L, int i, int& bA, int& bB, bool& self) {
@@ -1080,78 +1100,6 @@ template <class P, class Ld, class Out> NSB_HD void zg_inverse(int L, cplx* buf,
         fft_pass_last<P, INV, 1>(bA, buf, va);
         fft_pass_last<P, INV, 1>(bB, buf, vb);
         out(bA, bB, va, vb);         // va[j] = x(bA + j M1), vb[j] = x(bB + j M1); only the lane's own rows of buf may be overwritten
-    }
-}
-
-template <class P>
-__global__ void __launch_bounds__(ZGenCfg<P>::FUSED_THREADS, 2) k_zg_fused(const ZArgs a) {
-    constexpr int NP = P::NPAD, NPR = ZGenCfg<P>::NPR;
-    extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
-    cplx* sm = reinterpret_cast<cplx*>(nsb_smem_raw);
-    const int t = threadIdx.x >> 5, L = threadIdx.x & 31;
-    const cplx* __restrict__ tw = a.tw;
-    const int kzin = a.kz_in, kzout = a.kz_out;
-    const int i1 = (t + 1) % 3, i2 = (t + 2) % 3;
-    const int fu = i1, fw = 3 + i2;
-    for (long long pr = blockIdx.x; pr < a.npairs; pr += gridDim.x) {
-        const long long roff = 2 * pr * a.rs;
-        cplx c[NPR][16];
-#pragma unroll 1
-        for (int ff = 0; ff < 2; ++ff) {
-            const int f = ff ? fw : fu;
-            cplx* buf = sm + f * NP;
-            const cplx* ra = a.base + f * a.fstride + roff;
-            const cplx* rb = ra + a.rs;
-            zg_inverse<P>(L, buf, tw, [&](int k, cplx& A, cplx& B) {
-                if (k < kzin) { A = NSB_LDCG(ra + k); B = NSB_LDCG(rb + k); }
-                else { A = mk(0.0, 0.0); B = mk(0.0, 0.0); }
-            }, [&](int bA, int bB, const cplx* va, const cplx* vb) {
-                const int rbA = fft_row_base<P>(bA), rbB = fft_row_base<P>(bB);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { buf[rbA + j] = va[j]; buf[rbB + j] = vb[j]; }   // in place: point bA + j M1 lives at rbA + j
-            });
-        }
-        __syncthreads();                                   // the six real-space fields of the pair are complete
-        const cplx* u1 = sm + i1 * NP;
-        const cplx* u2 = sm + i2 * NP;
-        const cplx* v1 = sm + (3 + i1) * NP;
-        const cplx* v2 = sm + (3 + i2) * NP;
-#pragma unroll
-        for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self;
-            zg_pair<P>(L, i, bA, bB, self);
-            const int rbA = fft_row_base<P>(bA), rbB = fft_row_base<P>(bB);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) c[i][j] = cross_comp(u1[rbA + j], v2[rbA + j], u2[rbA + j], v1[rbA + j]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) c[i][8 + j] = cross_comp(u1[rbB + j], v2[rbB + j], u2[rbB + j], v1[rbB + j]);
-            zg_bfly_pair<FWD>(self, c[i], c[i] + 8, zg_load_tw1<P>(L, i, tw));
-        }
-        __syncthreads();                                   // all reads of the real-space fields are done
-        cplx* buf = sm + fu * NP;
-#pragma unroll
-        for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self;
-            zg_pair<P>(L, i, bA, bB, self);
-            zw_scatter_pair<P>(bA, bB, buf, c[i], c[i] + 8);
-        }
-        __syncwarp();
-        zg_pass2<P, FWD>(L, buf, tw);
-        __syncwarp();
-        cplx* oa = a.base + t * a.fstride + roff;
-        cplx* ob = oa + a.rs;
-#pragma unroll
-        for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self;
-            zg_pair<P>(L, i, bA, bB, self);
-            cplx va[8], vb[8];
-            fft_pass_last<P, FWD, 1>(bA, buf, va);
-            fft_pass_last<P, FWD, 1>(bB, buf, vb);
-            zg_unpack_store<P>(bA, bB, self, va, vb, [&](int k, cplx A, cplx B) {
-                if (k < kzout) { oa[k] = A; ob[k] = B; }
-            });
-        }
-        __syncwarp();
     }
 }
 

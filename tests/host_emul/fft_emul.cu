@@ -304,8 +304,9 @@ template <class P> int check_fused_warp() {
     return err / nrm < 1e-13 ? 0 : 1;
 }
 
-// Emulates k_zg_fused (general warp-per-transform kernel: NPR mirrored pairs per lane, radix-8 or radix-16 middle pass,
-// twiddle powers formed on the fly) phase by phase with the kernel's own helpers.
+// The general one-warp helpers (zg_*: NPR mirrored pairs per lane, radix-8 or radix-16 middle pass, twiddle powers formed
+// on the fly) that the stand-alone passes k_zg_c2r / k_zg_r2c are built from, run phase by phase through a fused
+// c2r -> cross product -> r2c data flow.
 template <class P> int check_fused_gen() {
     constexpr int N = P::N, NP = P::NPAD, NPR = ZGenCfg<P>::NPR;
     std::vector<cplx> tw(N), sm(6 * NP, mk(1e300, 1e300));
@@ -403,8 +404,7 @@ template <class P> int check_fused_gen() {
 // pair, lanes emulated one after the other between the __syncwarp points.  c2r against a long double DFT, then r2c of the
 // exact real rows against a long double DFT.
 template <class P> int check_warp_passes() {
-    typedef ZWarpPassCfg<P> Cfg;
-    constexpr int N = P::N, NP = P::NPAD, LPT = Cfg::LPT;
+    constexpr int N = P::N, NP = P::NPAD, LPT = P::M1 / 2;
     std::vector<cplx> tw(N), buf(NP, mk(1e300, 1e300));
     for (int m = 0; m < N; ++m) {
         long double a = -2.0L * 3.14159265358979323846264338327950288L * m / N;
@@ -412,13 +412,12 @@ template <class P> int check_warp_passes() {
     }
     std::vector<cplx> rows[2];
     for (int r = 0; r < 2; ++r) { rows[r].resize(N / 2 + 1); for (auto& z : rows[r]) z = mk(frand(), frand()); }
-    auto w2 = [&](int l, int j) { return tw[P::R1 * (l % P::M2) * j]; };
     // ---- c2r
     for (int l = 0; l < LPT; ++l) {
         cplx w1[7]; zw_load_tw1<P>(l, tw.data(), w1);
         zw_inv_pass1<P>(l, buf.data(), w1, [&](int k, cplx& A, cplx& B) { A = rows[0][k]; B = rows[1][k]; });
     }
-    for (int l = 0; l < LPT; ++l) zw_pass2<P, INV>(l, buf.data(), w2(l, 1), w2(l, 2), w2(l, 4));
+    for (int l = 0; l < LPT; ++l) zw_pass2<P, INV>(l, buf.data(), ZwTw2<P>(l, tw.data()));
     std::vector<double> got[2]; got[0].assign(N, 1e300); got[1].assign(N, 1e300);
     for (int l = 0; l < LPT; ++l) {
         int bA, bB; bool self; zw_lane_pair<P>(l, bA, bB, self);
@@ -460,7 +459,7 @@ template <class P> int check_warp_passes() {
         int bA, bB; bool self; zw_lane_pair<P>(l, bA, bB, self);
         zw_scatter_pair<P>(bA, bB, buf.data(), &creg[l * 16], &creg[l * 16 + 8]);
     }
-    for (int l = 0; l < LPT; ++l) zw_pass2<P, FWD>(l, buf.data(), w2(l, 1), w2(l, 2), w2(l, 4));
+    for (int l = 0; l < LPT; ++l) zw_pass2<P, FWD>(l, buf.data(), ZwTw2<P>(l, tw.data()));
     for (int l = 0; l < LPT; ++l) {
         cplx va[8], vb[8];
         zw_last_pair<P, FWD>(l, buf.data(), va, vb);
@@ -512,6 +511,7 @@ int main() {
     bad += check_warp_passes<ZWPlan<512>::type>();
     bad += check_warp_passes<ZWPlan<256>::type>();
     bad += check_warp_passes<ZWPlan<128>::type>();
+    bad += check_warp_passes<FftPlan<1024, 8, 16, 8>>();   // lane program of the two-warp fused kernel at 1024
     bad += check_fused_gen<FftPlan<512, 8, 8, 8>>();
     bad += check_fused_gen<FftPlan<1024, 8, 16, 8>>();
     bad += check_pack<16>();
