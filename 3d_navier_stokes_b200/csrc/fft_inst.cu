@@ -21,8 +21,7 @@
 #define NSB_HAVE_ZFW 0
 #define NSB_HAVE_ZPW 0
 #endif
-// 1024 = 8 x 16 x 8: the fused kernel with two warps per transform, the stand-alone passes in the general one-warp form (two
-// mirrored pairs per lane, radix-16 middle pass)
+// 1024 = 8 x 16 x 8: the same kernels with two warps per transform (radix-16 middle pass)
 #if NSB_N == 1024
 #define NSB_HAVE_ZG 1
 #else
@@ -38,6 +37,11 @@ typedef ZWPlan<NSB_N>::type ZW;
 #endif
 #if NSB_HAVE_ZG
 typedef FftPlan<NSB_N, 8, 16, 8> ZG;
+#define NSB_ZG_C2R k_z_c2r_w<ZG>
+#define NSB_ZG_R2C k_z_r2c_w<ZG>
+#define NSB_ZG_PASS_THREADS ZWarpPassCfg<ZG>::THREADS
+#define NSB_ZG_PASS_SMEM ZWarpPassCfg<ZG>::SMEM
+#define NSB_ZG_PASS_PAIRS ZWarpPassCfg<ZG>::PAIRS
 #endif
 constexpr int ST = StridedCfg<NSB_N>::T, STP = StridedCfg<NSB_N>::TP;
 constexpr size_t kStridedSmem = (size_t)BP::NPAD * ST * sizeof(cplx);
@@ -76,9 +80,9 @@ int setup() {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_z_fused_w<ZG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZWarpCfg<ZG>::SMEM);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_zg_c2r<ZG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZGenCfg<ZG>::PASS_SMEM);
+    e = cudaFuncSetAttribute(NSB_ZG_C2R, cudaFuncAttributeMaxDynamicSharedMemorySize, NSB_ZG_PASS_SMEM);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_zg_r2c<ZG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZGenCfg<ZG>::PASS_SMEM);
+    e = cudaFuncSetAttribute(NSB_ZG_R2C, cudaFuncAttributeMaxDynamicSharedMemorySize, NSB_ZG_PASS_SMEM);
 #endif
     return (int)e;
 }
@@ -208,8 +212,8 @@ int zlaunch(int which, const ZArgs* a, int nfields, int grid_x, cudaStream_t s) 
 #endif
 #if NSB_HAVE_ZG
     else if (which == NSB_Z_FUSED_W) k_z_fused_w<ZG><<<dim3(grid_x), ZWarpCfg<ZG>::THREADS, ZWarpCfg<ZG>::SMEM, s>>>(*a);
-    else if (which == NSB_Z_C2R_W) k_zg_c2r<ZG><<<dim3(grid_x, nfields), ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM, s>>>(*a);
-    else if (which == NSB_Z_R2C_W) k_zg_r2c<ZG><<<dim3(grid_x, nfields), ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM, s>>>(*a);
+    else if (which == NSB_Z_C2R_W) NSB_ZG_C2R<<<dim3(grid_x, nfields), NSB_ZG_PASS_THREADS, NSB_ZG_PASS_SMEM, s>>>(*a);
+    else if (which == NSB_Z_R2C_W) NSB_ZG_R2C<<<dim3(grid_x, nfields), NSB_ZG_PASS_THREADS, NSB_ZG_PASS_SMEM, s>>>(*a);
 #endif
     else k_z_fused<ZF><<<dim3(grid_x), ZFusedCfg<ZF>::THREADS, kZFusedSmem, s>>>(*a);
     return (int)cudaGetLastError();
@@ -229,8 +233,8 @@ int zocc(int which) {
 #endif
 #if NSB_HAVE_ZG
     else if (which == NSB_Z_FUSED_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused_w<ZG>, ZWarpCfg<ZG>::THREADS, ZWarpCfg<ZG>::SMEM);
-    else if (which == NSB_Z_C2R_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zg_c2r<ZG>, ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM);
-    else if (which == NSB_Z_R2C_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zg_r2c<ZG>, ZGenCfg<ZG>::PASS_THREADS, ZGenCfg<ZG>::PASS_SMEM);
+    else if (which == NSB_Z_C2R_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, NSB_ZG_C2R, NSB_ZG_PASS_THREADS, NSB_ZG_PASS_SMEM);
+    else if (which == NSB_Z_R2C_W) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, NSB_ZG_R2C, NSB_ZG_PASS_THREADS, NSB_ZG_PASS_SMEM);
 #endif
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_z_fused<ZF>, ZFusedCfg<ZF>::THREADS, kZFusedSmem);
     return n;
@@ -243,7 +247,7 @@ int zocc(int which) {
 #define NSB_ZPW_PAIRS ZWarpPassCfg<ZW>::PAIRS
 #elif NSB_HAVE_ZG
 #define NSB_ZFW_PAIRS 1
-#define NSB_ZPW_PAIRS 4
+#define NSB_ZPW_PAIRS NSB_ZG_PASS_PAIRS
 #else
 #define NSB_ZFW_PAIRS 0
 #define NSB_ZPW_PAIRS 0

@@ -15,8 +15,7 @@
 //                   transforms of :656/:658 and :683).
 //   k_z_fused_w, k_z_c2r_w, k_z_r2c_w  the same z kernels with Hermitian-mirrored butterfly pairs per lane and warp-level
 //                   synchronisation (second generation): one warp per transform at N = 512, two / four transforms side by
-//                   side in a warp at 256 / 128, two warps per transform (named barrier) for the fused kernel at 1024;
-//                   k_zg_c2r, k_zg_r2c: the stand-alone passes at 1024 (one warp, two mirrored pairs per lane).
+//                   side in a warp at 256 / 128, two warps per transform (named barrier) at 1024.
 #pragma once
 #include <cuda.h>
 #include "fft_core.cuh"
@@ -880,20 +879,22 @@ __global__ void __launch_bounds__(ZWarpCfg<P>::THREADS, ZWarpCfg<P>::MINB) k_z_f
 // M1 = 32 or 16 butterflies per pass (N = 256 = 8 x 4 x 8, N = 128 = 8 x 2 x 8) needs only 16 or 8 lanes per transform:
 // the warp then transforms SUB = 2 or 4 pencil pairs side by side, each in its own buffer.
 template <class P> struct ZWarpPassCfg {
-    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && (P::M1 == 64 || P::M1 == 32 || P::M1 == 16) && P::M2 == 8,
-                  "warp-per-pair z passes: plan 8 x (8 | 4 | 2) x 8");
-    static constexpr int LPT = P::M1 / 2;             // lanes per transform: lane l owns the mirrored pair (l, M1 - l)
-    static constexpr int SUB = 32 / LPT;              // transforms side by side in a warp
-    static constexpr int WARPS = 4, THREADS = 32 * WARPS, PAIRS = WARPS * SUB, SMEM = PAIRS * P::NPAD * 16;
+    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && (P::M1 == 128 || P::M1 == 64 || P::M1 == 32 || P::M1 == 16) && P::M2 == 8,
+                  "warp-per-pair z passes: plan 8 x (16 | 8 | 4 | 2) x 8");
+    static constexpr int LPT = ZWarpCfg<P>::LPT, WPT = ZWarpCfg<P>::WPT, SUB = ZWarpCfg<P>::SUB;   // see ZWarpCfg
+    static constexpr int WARPS = 4, THREADS = 32 * WARPS;
+    static constexpr int TRANSFORMS = WARPS / WPT;    // transforms in flight per CTA (N = 1024: two, each by a pair of warps)
+    static constexpr int PAIRS = TRANSFORMS * SUB, SMEM = PAIRS * P::NPAD * 16;
 };
+
 template <class P>
 __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const ZArgs a) {
     typedef ZWarpPassCfg<P> Cfg;
-    constexpr int LPT = Cfg::LPT, SUB = Cfg::SUB;
+    constexpr int LPT = Cfg::LPT, SUB = Cfg::SUB, WPT = Cfg::WPT;
     extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
-    const int wp = threadIdx.x >> 5, L = threadIdx.x & 31;
+    const int tr = threadIdx.x / (32 * WPT), L = threadIdx.x % (32 * WPT);   // transform slot of the CTA, lane within it
     const int l = L % LPT, sub = L / LPT;
-    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + (wp * SUB + sub) * P::NPAD;
+    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + (tr * SUB + sub) * P::NPAD;
     cplx* F = a.base + (long long)blockIdx.y * a.fstride;
     const cplx* __restrict__ tw = a.tw;
     const int kzin = a.kz_in;
@@ -902,7 +903,7 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const Z
     cplx w1[7];
     zw_load_tw1<P>(l, tw, w1);
     const ZwTw2<P> w2(l, tw);                          // see k_z_fused_w
-    for (long long p0 = ((long long)blockIdx.x * Cfg::WARPS + wp) * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * Cfg::PAIRS) {
+    for (long long p0 = ((long long)blockIdx.x * Cfg::TRANSFORMS + tr) * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * Cfg::PAIRS) {
         const long long pr = p0 + sub;
         const bool ok = pr < a.npairs;                   // the last warp trip may hold fewer than SUB pairs
         cplx* ra = F + 2 * (ok ? pr : p0) * a.rs;
@@ -911,9 +912,9 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const Z
             if (k < kzin && ok) { A = NSB_LDCG(ra + k); B = NSB_LDCG(rb + k); }
             else { A = mk(0.0, 0.0); B = mk(0.0, 0.0); }
         });
-        __syncwarp();
+        zw_tsync<WPT>(tr);
         zw_pass2<P, INV>(l, buf, w2);
-        __syncwarp();
+        zw_tsync<WPT>(tr);
         cplx va[8], vb[8];
         zw_last_pair<P, INV>(l, buf, va, vb);
         if (ok) {
@@ -925,18 +926,18 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_c2r_w(const Z
                 oa[bB + j * P::M1] = vb[j].x; ob[bB + j * P::M1] = vb[j].y;
             }
         }
-        __syncwarp();
+        zw_tsync<WPT>(tr);
     }
 }
 
 template <class P>
 __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const ZArgs a) {
     typedef ZWarpPassCfg<P> Cfg;
-    constexpr int LPT = Cfg::LPT, SUB = Cfg::SUB;
+    constexpr int LPT = Cfg::LPT, SUB = Cfg::SUB, WPT = Cfg::WPT;
     extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
-    const int wp = threadIdx.x >> 5, L = threadIdx.x & 31;
+    const int tr = threadIdx.x / (32 * WPT), L = threadIdx.x % (32 * WPT);   // transform slot of the CTA, lane within it
     const int l = L % LPT, sub = L / LPT;
-    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + (wp * SUB + sub) * P::NPAD;
+    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + (tr * SUB + sub) * P::NPAD;
     cplx* F = a.base + (long long)blockIdx.y * a.fstride;
     const cplx* __restrict__ tw = a.tw;
     const int kzout = a.kz_out;
@@ -945,7 +946,7 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const Z
     cplx w1[7];
     zw_load_tw1<P>(l, tw, w1);
     const ZwTw2<P> w2(l, tw);                          // see k_z_fused_w
-    for (long long p0 = ((long long)blockIdx.x * Cfg::WARPS + wp) * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * Cfg::PAIRS) {
+    for (long long p0 = ((long long)blockIdx.x * Cfg::TRANSFORMS + tr) * SUB; p0 < a.npairs; p0 += (long long)gridDim.x * Cfg::PAIRS) {
         const long long pr = p0 + sub;
         const bool ok = pr < a.npairs;
         cplx* ra = F + 2 * (ok ? pr : p0) * a.rs;
@@ -960,221 +961,15 @@ __global__ void __launch_bounds__(ZWarpPassCfg<P>::THREADS, 3) k_z_r2c_w(const Z
         }
         zw_bfly_pair<FWD>(self, ca, cb, w1);
         zw_scatter_pair<P>(bA, bB, buf, ca, cb);
-        __syncwarp();
+        zw_tsync<WPT>(tr);
         zw_pass2<P, FWD>(l, buf, w2);
-        __syncwarp();
+        zw_tsync<WPT>(tr);
         zw_last_pair<P, FWD>(l, buf, ca, cb);
-        __syncwarp();                                    // in place: every lane has read the real rows before the spectra overwrite them
+        zw_tsync<WPT>(tr);                                    // in place: every lane has read the real rows before the spectra overwrite them
         zw_unpack_store<P>(l, ca, cb, [&](int k, cplx A, cplx B) {
             if (k < kzout && ok) { ra[k] = A; rb[k] = B; }
         });
-        __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------ warp-per-pair z passes, general form
-// The stand-alone passes for plans 8 x R2 x 8 with M1 = N/8 = 64 * NPR butterflies per pass (N = 1024: 8 x 16 x 8, two
-// mirrored pairs per lane, radix-16 middle pass; the fused kernel at 1024 is k_z_fused_w with two warps per transform).  All twiddles are formed on the fly from the powers 1, 2, 4 (, 8) of the
-// butterfly's base twiddle, so the register file has room for the second pair.  Pair i of lane L: i = 0 is (L, M1 - L)
-// (lane 0: the self-mirrored butterflies 0 and M1/2), i >= 1 is (32 i + L, M1 - 32 i - L).
-template <class P> struct ZGenCfg {
-    static_assert(P::R1 == 8 && P::RL == 8 && P::PASSES == 3 && P::M1 % 64 == 0 && P::M2 == 8 && (P::R2 == 8 || P::R2 == 16),
-                  "general warp-per-transform kernels: plan 8 x (8 | 16) x 8");
-    static constexpr int NPR = P::M1 / 64;
-    static constexpr int WARPS = 4, PASS_THREADS = 32 * WARPS, PASS_SMEM = WARPS * P::NPAD * 16;
-};
-template <class P> NSB_HD void zg_pair(int L, int i, int& bA, int& bB, bool& self) {
-    self = (L == 0 && i == 0);
-    bA = 32 * i + L;
-    bB = self ? P::M1 / 2 : P::M1 - bA;
-}
-struct ZgTw { cplx a, b, c; };     // W^t, W^2t, W^4t of the pair's base index t
-template <class P> NSB_HD ZgTw zg_load_tw1(int L, int i, const cplx* __restrict__ tw) {
-    const int t = (L == 0 && i == 0) ? P::M1 / 2 : 32 * i + L;
-    ZgTw w; w.a = tw[t]; w.b = tw[2 * t]; w.c = tw[4 * t];
-    return w;
-}
-template <int DIR> NSB_HD void zg_bfly_pair(bool self, cplx* xa, cplx* xb, const ZgTw& w) {
-    Dft<8, DIR>::run(xa);
-    if (!self) twiddle8_base<DIR>(xa, w.a, w.b, w.c);
-    cplx y[8];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) y[n] = xb[(n + 7) & 7];
-    Dft<8, DIR>::run(y);
-    twiddle8_base<-DIR>(y, w.a, w.b, w.c);
-#pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) xb[k1] = y[k1];
-}
-// half-spectrum entries -> packed inputs of the pair (see zw_inv_pass1)
-template <class P, class Ld> NSB_HD void zg_load_pair(int bA, int bB, bool self, cplx* xa, cplx* xb, Ld ld) {
-    constexpr int M1 = P::M1;
-    if (!self) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cplx A, B;
-            ld(bA + j * M1, A, B);
-            xa[j] = zw_pack(A, B); xb[7 - j] = zw_packc(A, B);
-            ld(bB + j * M1, A, B);
-            xb[j] = zw_pack(A, B); xa[7 - j] = zw_packc(A, B);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j <= 4; ++j) {
-            cplx A, B;
-            ld(j * M1, A, B);
-            if (j == 0 || j == 4) { A.y = 0.0; B.y = 0.0; }
-            xa[j] = zw_pack(A, B);
-            if (j >= 1 && j <= 3) xa[8 - j] = zw_packc(A, B);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cplx A, B;
-            ld(M1 / 2 + j * M1, A, B);
-            xb[j] = zw_pack(A, B); xb[7 - j] = zw_packc(A, B);
-        }
-    }
-}
-template <class P, class St> NSB_HD void zg_unpack_store(int bA, int bB, bool self, const cplx* va, const cplx* vb, St st) {
-    constexpr int M1 = P::M1;
-    if (!self) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cplx A, B;
-            unpack_pair(va[j], vb[7 - j], A, B);
-            st(bA + j * M1, A, B);
-            unpack_pair(vb[j], va[7 - j], A, B);
-            st(bB + j * M1, A, B);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j <= 4; ++j) {
-            cplx A, B;
-            unpack_pair(va[j], va[(8 - j) & 7], A, B);
-            st(j * M1, A, B);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cplx A, B;
-            unpack_pair(vb[j], vb[7 - j], A, B);
-            st(M1 / 2 + j * M1, A, B);
-        }
-    }
-}
-// middle pass of one transform by the warp (NB2 / 32 butterflies per lane, all with the lane's m2 = L % 8)
-template <class P, int DIR> NSB_HD void zg_pass2(int L, cplx* buf, const cplx* __restrict__ tw) {
-    const int t = P::R1 * (L % P::M2);
-    if constexpr (P::R2 == 16) {
-        const cplx w1 = tw[t], w2 = tw[2 * t], w4 = tw[4 * t], w8 = tw[8 * t];
-#pragma unroll 1
-        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r16_base<P, DIR, 1>(L + 32 * i, buf, w1, w2, w4, w8);
-    } else {
-        const cplx w1 = tw[t], w2 = tw[2 * t], w4 = tw[4 * t];
-#pragma unroll 1
-        for (int i = 0; i < P::NB2 / 32; ++i) fft_pass2_r8_base<P, DIR, 1>(L + 32 * i, buf, w1, w2, w4);
-    }
-}
-// inverse transform of one packed pencil pair by the warp; real-space outputs written back in place (own rows)
-template <class P, class Ld, class Out> NSB_HD void zg_inverse(int L, cplx* buf, const cplx* __restrict__ tw, Ld ld, Out out) {
-    constexpr int NPR = ZGenCfg<P>::NPR;
-#pragma unroll 1
-    for (int i = 0; i < NPR; ++i) {
-        int bA, bB; bool self;
-        zg_pair<P>(L, i, bA, bB, self);
-        cplx xa[8], xb[8];
-        zg_load_pair<P>(bA, bB, self, xa, xb, ld);
-        zg_bfly_pair<INV>(self, xa, xb, zg_load_tw1<P>(L, i, tw));
-        zw_scatter_pair<P>(bA, bB, buf, xa, xb);
-    }
-#ifdef __CUDA_ARCH__
-    __syncwarp();
-#endif
-    zg_pass2<P, INV>(L, buf, tw);
-#ifdef __CUDA_ARCH__
-    __syncwarp();
-#endif
-#pragma unroll 1
-    for (int i = 0; i < NPR; ++i) {
-        int bA, bB; bool self;
-        zg_pair<P>(L, i, bA, bB, self);
-        cplx va[8], vb[8];
-        fft_pass_last<P, INV, 1>(bA, buf, va);
-        fft_pass_last<P, INV, 1>(bB, buf, vb);
-        out(bA, bB, va, vb);         // va[j] = x(bA + j M1), vb[j] = x(bB + j M1); only the lane's own rows of buf may be overwritten
-    }
-}
-
-template <class P>
-__global__ void __launch_bounds__(ZGenCfg<P>::PASS_THREADS, 3) k_zg_c2r(const ZArgs a) {
-    constexpr int WARPS = ZGenCfg<P>::WARPS, NPR = ZGenCfg<P>::NPR;
-    extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
-    const int wp = threadIdx.x >> 5, L = threadIdx.x & 31;
-    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + wp * P::NPAD;
-    cplx* F = a.base + (long long)blockIdx.y * a.fstride;
-    const cplx* __restrict__ tw = a.tw;
-    const int kzin = a.kz_in;
-    for (long long pr = (long long)blockIdx.x * WARPS + wp; pr < a.npairs; pr += (long long)gridDim.x * WARPS) {
-        cplx* ra = F + 2 * pr * a.rs;
-        cplx* rb = ra + a.rs;
-        double* oa = reinterpret_cast<double*>(ra);      // in place: all entries were loaded before the first pass-2 butterfly
-        double* ob = reinterpret_cast<double*>(rb);
-        zg_inverse<P>(L, buf, tw, [&](int k, cplx& A, cplx& B) {
-            if (k < kzin) { A = NSB_LDCG(ra + k); B = NSB_LDCG(rb + k); }
-            else { A = mk(0.0, 0.0); B = mk(0.0, 0.0); }
-        }, [&](int bA, int bB, const cplx* va, const cplx* vb) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                oa[bA + j * P::M1] = va[j].x; ob[bA + j * P::M1] = va[j].y;
-                oa[bB + j * P::M1] = vb[j].x; ob[bB + j * P::M1] = vb[j].y;
-            }
-        });
-        __syncwarp();
-        (void)NPR;
-    }
-}
-
-template <class P>
-__global__ void __launch_bounds__(ZGenCfg<P>::PASS_THREADS, 3) k_zg_r2c(const ZArgs a) {
-    constexpr int WARPS = ZGenCfg<P>::WARPS, NPR = ZGenCfg<P>::NPR;
-    extern __shared__ __align__(16) unsigned char nsb_smem_raw[];
-    const int wp = threadIdx.x >> 5, L = threadIdx.x & 31;
-    cplx* buf = reinterpret_cast<cplx*>(nsb_smem_raw) + wp * P::NPAD;
-    cplx* F = a.base + (long long)blockIdx.y * a.fstride;
-    const cplx* __restrict__ tw = a.tw;
-    const int kzout = a.kz_out;
-    for (long long pr = (long long)blockIdx.x * WARPS + wp; pr < a.npairs; pr += (long long)gridDim.x * WARPS) {
-        cplx* ra = F + 2 * pr * a.rs;
-        cplx* rb = ra + a.rs;
-        const double* ia = reinterpret_cast<const double*>(ra);
-        const double* ib = reinterpret_cast<const double*>(rb);
-#pragma unroll 1
-        for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self;
-            zg_pair<P>(L, i, bA, bB, self);
-            cplx ca[8], cb[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                ca[j] = mk(NSB_LDCG(ia + bA + j * P::M1), NSB_LDCG(ib + bA + j * P::M1));
-                cb[j] = mk(NSB_LDCG(ia + bB + j * P::M1), NSB_LDCG(ib + bB + j * P::M1));
-            }
-            zg_bfly_pair<FWD>(self, ca, cb, zg_load_tw1<P>(L, i, tw));
-            zw_scatter_pair<P>(bA, bB, buf, ca, cb);
-        }
-        __syncwarp();
-        zg_pass2<P, FWD>(L, buf, tw);
-        __syncwarp();
-        // in place: every lane read its real rows before the first __syncwarp above, so the spectra may overwrite them now
-#pragma unroll 1
-        for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self;
-            zg_pair<P>(L, i, bA, bB, self);
-            cplx va[8], vb[8];
-            fft_pass_last<P, FWD, 1>(bA, buf, va);
-            fft_pass_last<P, FWD, 1>(bB, buf, vb);
-            zg_unpack_store<P>(bA, bB, self, va, vb, [&](int k, cplx A, cplx B) {
-                if (k < kzout) { ra[k] = A; rb[k] = B; }
-            });
-        }
-        __syncwarp();
+        zw_tsync<WPT>(tr);
     }
 }
 

@@ -304,102 +304,6 @@ template <class P> int check_fused_warp() {
     return err / nrm < 1e-13 ? 0 : 1;
 }
 
-// The general one-warp helpers (zg_*: NPR mirrored pairs per lane, radix-8 or radix-16 middle pass, twiddle powers formed
-// on the fly) that the stand-alone passes k_zg_c2r / k_zg_r2c are built from, run phase by phase through a fused
-// c2r -> cross product -> r2c data flow.
-template <class P> int check_fused_gen() {
-    constexpr int N = P::N, NP = P::NPAD, NPR = ZGenCfg<P>::NPR;
-    std::vector<cplx> tw(N), sm(6 * NP, mk(1e300, 1e300));
-    for (int m = 0; m < N; ++m) {
-        long double a = -2.0L * 3.14159265358979323846264338327950288L * m / N;
-        tw[m] = mk((double)cosl(a), (double)sinl(a));
-    }
-    std::vector<cplx> rows[6][2], outA[3], outB[3];
-    for (int f = 0; f < 6; ++f) for (int r = 0; r < 2; ++r) { rows[f][r].resize(N / 2 + 1); for (auto& z : rows[f][r]) z = mk(frand(), frand()); }
-    for (int t = 0; t < 3; ++t) { outA[t].assign(N / 2 + 1, mk(1e300, 1e300)); outB[t].assign(N / 2 + 1, mk(1e300, 1e300)); }
-    for (int f = 0; f < 6; ++f) {
-        cplx* buf = sm.data() + f * NP;
-        for (int L = 0; L < 32; ++L) for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self; zg_pair<P>(L, i, bA, bB, self);
-            cplx xa[8], xb[8];
-            zg_load_pair<P>(bA, bB, self, xa, xb, [&](int k, cplx& A, cplx& B) { A = rows[f][0][k]; B = rows[f][1][k]; });
-            zg_bfly_pair<INV>(self, xa, xb, zg_load_tw1<P>(L, i, tw.data()));
-            zw_scatter_pair<P>(bA, bB, buf, xa, xb);
-        }
-        for (int L = 0; L < 32; ++L) zg_pass2<P, INV>(L, buf, tw.data());
-        std::vector<cplx> keep(32 * NPR * 16);
-        for (int L = 0; L < 32; ++L) for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self; zg_pair<P>(L, i, bA, bB, self);
-            fft_pass_last<P, INV, 1>(bA, buf, &keep[(L * NPR + i) * 16]);
-            fft_pass_last<P, INV, 1>(bB, buf, &keep[(L * NPR + i) * 16 + 8]);
-        }
-        for (int L = 0; L < 32; ++L) for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self; zg_pair<P>(L, i, bA, bB, self);
-            for (int j = 0; j < 8; ++j) { buf[fft_row_base<P>(bA) + j] = keep[(L * NPR + i) * 16 + j]; buf[fft_row_base<P>(bB) + j] = keep[(L * NPR + i) * 16 + 8 + j]; }
-        }
-    }
-    std::vector<double> real[6][2];
-    for (int f = 0; f < 6; ++f) for (int r = 0; r < 2; ++r) {
-        real[f][r].resize(N);
-        for (int n = 0; n < N; ++n) {
-            long double sacc = 0;
-            for (int k = 0; k < N; ++k) {
-                int kk = k <= N / 2 ? k : N - k;
-                long double ar = rows[f][r][kk].x, ai = (k <= N / 2 ? rows[f][r][kk].y : -rows[f][r][kk].y);
-                if (k == 0 || k == N / 2) ai = 0;
-                long double a = 2.0L * 3.14159265358979323846264338327950288L * ((long long)n * k % N) / N;
-                sacc += ar * cosl(a) - ai * sinl(a);
-            }
-            real[f][r][n] = (double)sacc;
-        }
-    }
-    std::vector<cplx> creg(3 * 32 * NPR * 16);
-    for (int t = 0; t < 3; ++t) for (int L = 0; L < 32; ++L) for (int i = 0; i < NPR; ++i) {
-        int bA, bB; bool self; zg_pair<P>(L, i, bA, bB, self);
-        const int i1 = (t + 1) % 3, i2 = (t + 2) % 3, rbA = fft_row_base<P>(bA), rbB = fft_row_base<P>(bB);
-        cplx* c = &creg[((t * 32 + L) * NPR + i) * 16];
-        for (int j = 0; j < 8; ++j) {
-            c[j] = cross_comp(sm[i1 * NP + rbA + j], sm[(3 + i2) * NP + rbA + j], sm[i2 * NP + rbA + j], sm[(3 + i1) * NP + rbA + j]);
-            c[8 + j] = cross_comp(sm[i1 * NP + rbB + j], sm[(3 + i2) * NP + rbB + j], sm[i2 * NP + rbB + j], sm[(3 + i1) * NP + rbB + j]);
-        }
-        zg_bfly_pair<FWD>(self, c, c + 8, zg_load_tw1<P>(L, i, tw.data()));
-    }
-    for (int t = 0; t < 3; ++t) {
-        cplx* buf = sm.data() + ((t + 1) % 3) * NP;
-        for (int L = 0; L < 32; ++L) for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self; zg_pair<P>(L, i, bA, bB, self);
-            cplx* c = &creg[((t * 32 + L) * NPR + i) * 16];
-            zw_scatter_pair<P>(bA, bB, buf, c, c + 8);
-        }
-        for (int L = 0; L < 32; ++L) zg_pass2<P, FWD>(L, buf, tw.data());
-        for (int L = 0; L < 32; ++L) for (int i = 0; i < NPR; ++i) {
-            int bA, bB; bool self; zg_pair<P>(L, i, bA, bB, self);
-            cplx va[8], vb[8];
-            fft_pass_last<P, FWD, 1>(bA, buf, va);
-            fft_pass_last<P, FWD, 1>(bB, buf, vb);
-            zg_unpack_store<P>(bA, bB, self, va, vb, [&](int k, cplx A, cplx B) { outA[t][k] = A; outB[t][k] = B; });
-        }
-    }
-    double err = 0, nrm = 0;
-    for (int t = 0; t < 3; ++t) for (int r = 0; r < 2; ++r) {
-        int i1 = (t + 1) % 3, i2 = (t + 2) % 3;
-        std::vector<double> c(N);
-        for (int n = 0; n < N; ++n) c[n] = real[i1][r][n] * real[3 + i2][r][n] - real[i2][r][n] * real[3 + i1][r][n];
-        for (int k = 0; k <= N / 2; ++k) {
-            long double sr = 0, si = 0;
-            for (int n = 0; n < N; ++n) {
-                long double a = -2.0L * 3.14159265358979323846264338327950288L * ((long long)n * k % N) / N;
-                sr += c[n] * cosl(a); si += c[n] * sinl(a);
-            }
-            cplx got = r == 0 ? outA[t][k] : outB[t][k];
-            err = fmax(err, fmax(fabs(got.x - (double)sr), fabs(got.y - (double)si)));
-            nrm = fmax(nrm, fmax(fabs((double)sr), fabs((double)si)));
-        }
-    }
-    printf("fused (general warp kernel) N=%d (%d,%d,%d): max rel err %.3e\n", N, P::R1, P::R2, P::R3, err / nrm);
-    return err / nrm < 1e-13 ? 0 : 1;
-}
-
 // stand-alone warp z passes (k_z_c2r_w / k_z_r2c_w) with LPT = M1/2 lanes per transform: the lane program of one pencil
 // pair, lanes emulated one after the other between the __syncwarp points.  c2r against a long double DFT, then r2c of the
 // exact real rows against a long double DFT.
@@ -511,9 +415,7 @@ int main() {
     bad += check_warp_passes<ZWPlan<512>::type>();
     bad += check_warp_passes<ZWPlan<256>::type>();
     bad += check_warp_passes<ZWPlan<128>::type>();
-    bad += check_warp_passes<FftPlan<1024, 8, 16, 8>>();   // lane program of the two-warp fused kernel at 1024
-    bad += check_fused_gen<FftPlan<512, 8, 8, 8>>();
-    bad += check_fused_gen<FftPlan<1024, 8, 16, 8>>();
+    bad += check_warp_passes<FftPlan<1024, 8, 16, 8>>();   // lane program of the two-warp kernels at 1024
     bad += check_pack<16>();
     bad += check_pack<64>();
     bad += check_pack<512>();
