@@ -10,7 +10,7 @@ struct FftOps {
     int strided_T;                 // kz columns per strided tile
     int tma_rows;                  // rows per TMA box of the strided tile load
     int pipe_T;                    // kz columns per tile of the persistent strided pass (0: not built)
-    int z_pairs_per_cta[NSB_Z_KINDS];   // row pairs per CTA for NSB_Z_C2R / _R2C / _FUSED and their warp-per-transform versions (0: kernel not built for this N)
+    int z_pairs_per_cta[NSB_Z_KINDS];   // row pairs per CTA (trip) for NSB_Z_C2R / _R2C / _FUSED and their warp-synchronised versions (0: not built for this N; < 0: built, not the default)
     int (*setup)(void);            // opt-in to large dynamic shared memory; returns cudaError_t
     // one c2c pass over `nfields` fields; grid = (ceil(nzv/T), n_outer_eff, nfields)
     // maps != NULL: tile loads through TMA tensor maps (natural layouts); NULL: cp.async path
@@ -22,7 +22,7 @@ struct FftOps {
     // persistent double-buffered strided pass (T = 4, TMA, natural input layout); NULL when not built for this N
     int (*strided_pipe)(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s);
     int (*pipe_occupancy)(void);
-    // persistent two-group ring pass (one CTA per SM, T = 8, TMA, natural input layout); NULL when not built for this N
+    // two-group ring pass (one CTA per SM, T = 8, TMA, natural input layout; free-running groups unless NSB200_RING_FR=0); NULL when not built for this N
     int (*strided_ring)(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s);
     // light variant of it (one group, two buffers, 256 threads) on a restricted persistent grid: link-bound store phases
     int (*strided_link)(int dir, const StridedArgs* a, const TmaMaps* maps, int n_outer_eff, int nfields, int max_ctas, cudaStream_t s);

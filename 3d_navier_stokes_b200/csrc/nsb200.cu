@@ -189,7 +189,7 @@ struct nsb200_ctx {
     int sm_count = 0;
     int zgrid[NSB_Z_KINDS] = {0, 0, 0, 0, 0, 0};
     bool z_warp_passes = false;    // stand-alone z passes: warp-per-transform kernels where built
-    int zf_kind = NSB_Z_FUSED;     // NSB_Z_FUSED_W (one warp per transform) where built; NSB200_ZF=old keeps the first generation
+    int zf_kind = NSB_Z_FUSED;     // NSB_Z_FUSED_W (warp-synchronised transforms) where built; NSB200_ZF=old keeps the first generation
     long launches = 0;
     double link_bytes = 0.0;       // bytes this rank has stored into peer memory (the fused slab exchange)
     size_t bytes = 0;

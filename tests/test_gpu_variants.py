@@ -103,10 +103,9 @@ def test_sub_warp_z_passes_agree_with_the_first_generation(n):
 
 
 def test_1024_warp_kernels_agree_with_the_first_generation():
-    """1024^3: fused z kernel with two warps per transform (named barrier between the passes) and stand-alone passes in the
-    general one-warp form (two mirrored pairs per lane, radix-16 middle pass, twiddle powers formed on the fly) against the
-    first-generation kernels (4-pass plan, table twiddles): two steps, energy to 1e-13.
-    (The 1-D lane programs themselves are checked against a long double DFT in tests/host_emul.)"""
+    """1024^3: fused z kernel and stand-alone z passes with two warps per transform (plan 8 x 16 x 8, named barrier between
+    the passes, twiddle powers formed on the fly) against the first-generation kernels (4-pass plan, table twiddles): two
+    steps, energy to 1e-13.  (The lane program itself is checked against a long double DFT in tests/host_emul.)"""
     _, e0 = run_variant(1024, {})
     _, e1 = run_variant(1024, {"NSB200_ZF": "old"})
     assert abs(e1 - e0) <= 1e-13 * abs(e0)
