@@ -83,28 +83,76 @@ static void ensure(void) {
 }
 /* Restart / external initial condition.  The reference parses `-z <file>` (utils.c:209-215)
  * but never reads it, and its `-i TESTING` branch of InitialConditions is an empty hook that leaves u_hat zero
- * (solver.c:1601-1605).  With both given, the file is taken as a raw dump of run_data->u_hat in the reference
- * layout ([local_Nx][Ny][Nz/2+1][3] double _Complex, this rank's slab at its offset) - the format the state is
- * written in by the I/O stand-in - and loaded before the first device upload.  Dealiasing is applied as
- * InitialConditions does for every other choice (solver.c:1630). */
+ * (solver.c:1601-1605).  With both given, the file is loaded before the first device upload:
+ *   - an HDF5 file (the reference's own Main_HDF_Data.h5): the u_hat dataset of its LAST /Iter_%05d group, this rank's
+ *     x-slab through a hyperslab selection - the mirror image of WriteGroupDataFourier (hdf5_funcs.c:1254-1279) with the
+ *     same compound {r,i} memory type (hdf5_funcs.c:1302-1333);
+ *   - anything else: a raw dump of run_data->u_hat in the reference layout ([Nx][Ny][Nz/2+1][3] double _Complex, this
+ *     rank's slab at its offset).
+ * Dealiasing is applied as InitialConditions does for every other choice (solver.c:1630). */
+static int file_is_hdf5(const char* path) {
+	static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+	unsigned char b[8];
+	FILE* f = fopen(path, "rb");
+	if (!f) return 0;
+	const int ok = fread(b, 1, 8, f) == 8 && !memcmp(b, sig, 8);
+	fclose(f);
+	return ok;
+}
+static void h5_die(const char* what, const char* path) {
+	fprintf(stderr, "\n["RED"ERROR"RESET"] --- %s in input file ["CYAN"%s"RESET"]\n-->> Exiting!!!\n", what, path);
+	exit(1);
+}
+static void load_state_from_hdf5(const char* path) {
+	const hsize_t Nzf = (hsize_t)(sys_vars->N[2] / 2 + 1);
+	hid_t file = H5Fopen(path, H5F_ACC_RDONLY, H5P_DEFAULT);
+	if (file < 0) h5_die("Unable to open / parse the HDF5 structures", path);
+	int last = -1;
+	char name[64];
+	for (int i = 0;; ++i) {                                     /* save indices are consecutive (solver.c:165-171) */
+		snprintf(name, sizeof name, "Iter_%05d", i);
+		if (H5Lexists(file, name, H5P_DEFAULT) > 0) last = i; else break;
+	}
+	if (last < 0) h5_die("No /Iter_%05d group", path);
+	snprintf(name, sizeof name, "Iter_%05d/u_hat", last);
+	hid_t dset = H5Dopen(file, name, H5P_DEFAULT);
+	if (dset < 0) h5_die("No u_hat dataset in the last group", path);
+	hid_t fspace = H5Dget_space(dset);
+	hsize_t dims[4] = {0, 0, 0, 0};
+	if (fspace < 0 || H5Sget_simple_extent_ndims(fspace) != 4 || H5Sget_simple_extent_dims(fspace, dims, NULL) != 4 ||
+	    dims[0] != (hsize_t)sys_vars->N[0] || dims[1] != (hsize_t)sys_vars->N[1] || dims[2] != Nzf || dims[3] != SYS_DIM)
+		h5_die("u_hat does not have the shape [Nx][Ny][Nz/2+1][3] of this run", path);
+	hsize_t start[4] = {(hsize_t)sys_vars->local_Nx_start, 0, 0, 0};
+	hsize_t count[4] = {(hsize_t)sys_vars->local_Nx, (hsize_t)sys_vars->N[1], Nzf, SYS_DIM};
+	hid_t mspace = H5Screate_simple(4, count, NULL);
+	hid_t ctype = H5Tcreate(H5T_COMPOUND, 2 * sizeof(double));
+	if (mspace < 0 || ctype < 0 || H5Tinsert(ctype, "r", 0, H5T_NATIVE_DOUBLE) < 0 || H5Tinsert(ctype, "i", sizeof(double), H5T_NATIVE_DOUBLE) < 0 ||
+	    H5Sselect_hyperslab(fspace, H5S_SELECT_SET, start, NULL, count, NULL) < 0 ||
+	    H5Dread(dset, ctype, mspace, fspace, H5P_DEFAULT, run_data->u_hat) < 0)
+		h5_die("Unable to read this rank's slab of u_hat", path);
+	H5Tclose(ctype); H5Sclose(mspace); H5Sclose(fspace); H5Dclose(dset); H5Fclose(file);
+}
 static void maybe_load_input_file(void) {
 	static int done = 0;
 	if (done) return;
 	done = 1;
 	if (strcmp(sys_vars->u0, "TESTING") || !strcmp(file_info->input_file_name, "NONE")) return;
-	const size_t n = (size_t)3 * sys_vars->local_Nx * sys_vars->N[1] * (sys_vars->N[2] / 2 + 1);
-	FILE* f = fopen(file_info->input_file_name, "rb");
-	if (!f) {
-		fprintf(stderr, "\n["RED"ERROR"RESET"] --- Unable to open input file ["CYAN"%s"RESET"]\n-->> Exiting!!!\n", file_info->input_file_name);
-		exit(1);
+	if (file_is_hdf5(file_info->input_file_name)) load_state_from_hdf5(file_info->input_file_name);
+	else {
+		const size_t n = (size_t)3 * sys_vars->local_Nx * sys_vars->N[1] * (sys_vars->N[2] / 2 + 1);
+		FILE* f = fopen(file_info->input_file_name, "rb");
+		if (!f) {
+			fprintf(stderr, "\n["RED"ERROR"RESET"] --- Unable to open input file ["CYAN"%s"RESET"]\n-->> Exiting!!!\n", file_info->input_file_name);
+			exit(1);
+		}
+		const long off = (long)(sizeof(fftw_complex) * 3 * (size_t)sys_vars->local_Nx_start * sys_vars->N[1] * (sys_vars->N[2] / 2 + 1));
+		if (fseek(f, off, SEEK_SET) || fread(run_data->u_hat, sizeof(fftw_complex), n, f) != n) {
+			fprintf(stderr, "\n["RED"ERROR"RESET"] --- Input file ["CYAN"%s"RESET"] is too short for a %ld^3 state\n-->> Exiting!!!\n",
+			        file_info->input_file_name, sys_vars->N[0]);
+			exit(1);
+		}
+		fclose(f);
 	}
-	const long off = (long)(sizeof(fftw_complex) * 3 * (size_t)sys_vars->local_Nx_start * sys_vars->N[1] * (sys_vars->N[2] / 2 + 1));
-	if (fseek(f, off, SEEK_SET) || fread(run_data->u_hat, sizeof(fftw_complex), n, f) != n) {
-		fprintf(stderr, "\n["RED"ERROR"RESET"] --- Input file ["CYAN"%s"RESET"] is too short for a %ld^3 state\n-->> Exiting!!!\n",
-		        file_info->input_file_name, sys_vars->N[0]);
-		exit(1);
-	}
-	fclose(f);
 	if (nsb200_apply_dealiasing(g_h, (double*)run_data->u_hat, SYS_DIM)) die("nsb200_apply_dealiasing");
 	g_host_newer = 1;
 }

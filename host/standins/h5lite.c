@@ -11,7 +11,11 @@
  * raw data on H5Fclose (the superblock then points at the new root).  A file created by this process can be reopened
  * with H5Fopen(H5F_ACC_RDWR) by the same process, which is what the reference does on every save (hdf5_funcs.c:538);
  * the raw data of the new save then overwrite the superseded metadata block, so nothing is wasted.
- * Single process, hyperslab selections with start/count only (all the reference uses), no chunking, no deletion. */
+ * Single process, hyperslab selections with start/count only (all the reference uses), no chunking, no deletion.
+ *
+ * Read side (restart from a saved state, host/nsb200_hooks.c): H5Fopen(H5F_ACC_RDONLY) of a file this process did not
+ * create parses the same structures back into the in-memory model (anything else in the file is refused), after which
+ * H5Lexists / H5Gopen / H5Dopen / H5Dget_space / H5Dread work on it; such a file is never written to. */
 #include "hdf5.h"
 #include "hdf5_hl.h"
 
@@ -35,7 +39,7 @@ typedef struct h5node {
     h5t type; int rank; hsize_t dims[MAXRANK]; uint64_t addr, bytes;   /* dataset */
     uint64_t ohdr, btree, heap;                                         /* filled while serialising */
 } h5node;
-typedef struct { char path[2048]; FILE* fp; h5node* root; uint64_t data_end; int open; } h5file;
+typedef struct { char path[2048]; FILE* fp; h5node* root; uint64_t data_end; int open; int readonly; } h5file;
 typedef struct { int rank; hsize_t dims[MAXRANK]; int sel; hsize_t start[MAXRANK], count[MAXRANK]; } h5space;
 
 enum { K_FREE = 0, K_FILE, K_GROUP, K_DSET, K_SPACE, K_TYPE, K_ATTR, K_PLIST };
@@ -299,6 +303,180 @@ static int flush_metadata(h5file* f) {
     return ok ? 0 : -1;
 }
 
+/* ------------------------------------------------------------------------------------------------ loader (read side) */
+typedef struct { FILE* fp; uint64_t eof; unsigned leaf_k, int_k; int depth; } h5rd;
+static uint64_t le(const unsigned char* p, int n) { uint64_t v = 0; for (int i = n - 1; i >= 0; --i) v = (v << 8) | p[i]; return v; }
+static int rd_at(h5rd* r, uint64_t at, void* dst, size_t n) {
+    if (at > r->eof || n > r->eof - at) return -1;
+    return (fseek(r->fp, (long)at, SEEK_SET) == 0 && fread(dst, 1, n, r->fp) == n) ? 0 : -1;
+}
+/* datatype message v1 at p (avail bytes): IEEE f64 LE, plain little-endian i32, compound of those; *used = encoded size */
+static int rd_datatype(const unsigned char* p, size_t avail, h5t* t, size_t* used) {
+    memset(t, 0, sizeof *t);
+    if (avail < 8) return -1;
+    const unsigned cls = p[0] & 15u, ver = p[0] >> 4;
+    const uint64_t size = le(p + 4, 4);
+    if (ver != 1) return -1;
+    if (cls == 0) {
+        if (avail < 12 || size != 4 || (p[1] & 1u) || !(p[1] & 8u) || le(p + 8, 2) != 0 || le(p + 10, 2) != 32) return -1;
+        t->kind = 0; t->size = 4; *used = 12;
+        return 0;
+    }
+    if (cls == 1) {
+        if (avail < 20 || size != 8 || p[1] != 0x20 || p[2] != 63 || le(p + 8, 2) != 0 || le(p + 10, 2) != 64 || p[12] != 52 || p[13] != 11 ||
+            p[14] != 0 || p[15] != 52 || le(p + 16, 4) != 1023) return -1;
+        t->kind = 1; t->size = 8; *used = 20;
+        return 0;
+    }
+    if (cls == 6) {
+        const unsigned nmem = p[1] | ((unsigned)p[2] << 8);
+        if (nmem < 1 || nmem > 8) return -1;
+        t->kind = 6; t->size = (size_t)size; t->nmem = (int)nmem;
+        size_t q = 8;
+        for (unsigned m = 0; m < nmem; ++m) {
+            const void* z = (q < avail) ? memchr(p + q, 0, avail - q) : NULL;
+            if (!z) return -1;
+            const size_t len = (size_t)((const unsigned char*)z - (p + q));
+            if (len > 31) return -1;
+            memcpy(t->mname[m], p + q, len + 1);
+            q += (len + 1 + 7) / 8 * 8;
+            if (q + 32 > avail || p[q + 4] != 0) return -1;           /* byte offset, dimensionality 0 (no array members) */
+            t->moff[m] = (size_t)le(p + q, 4);
+            q += 32;
+            h5t mt; size_t mu;
+            if (rd_datatype(p + q, avail - q, &mt, &mu) || mt.kind == 6 || t->moff[m] + mt.size > t->size) return -1;
+            t->mkind[m] = mt.kind;
+            q += mu;
+        }
+        *used = q;
+        return 0;
+    }
+    return -1;
+}
+static int rd_dataspace(const unsigned char* p, size_t avail, int* rank, hsize_t* dims) {
+    if (avail < 8 || p[0] != 1 || p[2] != 0 || p[1] < 1 || p[1] > MAXRANK || avail < 8 + 8u * p[1]) return -1;
+    *rank = p[1];
+    for (int d = 0; d < *rank; ++d) dims[d] = le(p + 8 + 8 * d, 8);
+    return 0;
+}
+static int rd_object(h5rd* r, uint64_t at, h5node* n);
+static int rd_name(h5rd* r, uint64_t heap_data, uint64_t heap_size, uint64_t off, char* out, size_t cap) {
+    if (off >= heap_size) return -1;
+    size_t n = (size_t)(heap_size - off < cap ? heap_size - off : cap);
+    if (rd_at(r, heap_data + off, out, n)) return -1;
+    return memchr(out, 0, n) ? 0 : -1;
+}
+static int rd_snod(h5rd* r, uint64_t at, uint64_t heap_data, uint64_t heap_size, h5node* g) {
+    unsigned char hd[8];
+    if (rd_at(r, at, hd, 8) || memcmp(hd, "SNOD", 4) || hd[4] != 1) return -1;
+    const unsigned cnt = (unsigned)le(hd + 6, 2);
+    if (cnt > 2 * r->leaf_k) return -1;
+    for (unsigned i = 0; i < cnt; ++i) {
+        unsigned char e[40];
+        char name[256];
+        if (rd_at(r, at + 8 + 40ull * i, e, 40) || rd_name(r, heap_data, heap_size, le(e, 8), name, sizeof name)) return -1;
+        if (find_child(g, name, strlen(name))) return -1;
+        h5node* c = add_child(g, name, strlen(name), 0);
+        if (rd_object(r, le(e + 8, 8), c)) return -1;
+    }
+    return 0;
+}
+static int rd_btree(h5rd* r, uint64_t at, uint64_t heap_data, uint64_t heap_size, h5node* g, int level_expect) {
+    unsigned char hd[24];
+    if (rd_at(r, at, hd, 24) || memcmp(hd, "TREE", 4) || hd[4] != 0) return -1;
+    const int level = hd[5];
+    const unsigned used = (unsigned)le(hd + 6, 2);
+    if (used > 2 * r->int_k || level > 8 || (level_expect >= 0 && level != level_expect)) return -1;
+    for (unsigned i = 0; i < used; ++i) {
+        unsigned char kid[8];
+        if (rd_at(r, at + 24 + 16ull * i + 8, kid, 8)) return -1;
+        if (level > 0 ? rd_btree(r, le(kid, 8), heap_data, heap_size, g, level - 1) : rd_snod(r, le(kid, 8), heap_data, heap_size, g)) return -1;
+    }
+    return 0;
+}
+static int rd_object(h5rd* r, uint64_t at, h5node* n) {
+    unsigned char hd[16];
+    if (++r->depth > 16 || rd_at(r, at, hd, 16) || hd[0] != 1) return -1;
+    const unsigned nmsg = (unsigned)le(hd + 2, 2);
+    const uint64_t hsize = le(hd + 8, 4);
+    if (hsize % 8 || hsize > (1u << 20)) return -1;
+    unsigned char* b = (unsigned char*)malloc(hsize ? hsize : 1);
+    int rc = rd_at(r, at + 16, b, hsize);
+    int have_space = 0, have_type = 0, have_layout = 0;
+    uint64_t stab_bt = UNDEF, stab_heap = UNDEF;
+    size_t p = 0;
+    unsigned seen = 0;
+    while (!rc && p + 8 <= hsize) {
+        const unsigned mtype = (unsigned)le(b + p, 2);
+        const size_t msize = (size_t)le(b + p + 2, 2);
+        const unsigned char* d = b + p + 8;
+        if (msize % 8 || p + 8 + msize > hsize) { rc = -1; break; }
+        if (mtype == 0x0001) { rc = rd_dataspace(d, msize, &n->rank, n->dims); have_space = 1; }
+        else if (mtype == 0x0003) { size_t u; rc = rd_datatype(d, msize, &n->type, &u); have_type = 1; }
+        else if (mtype == 0x0005) { if (msize < 4 || d[0] != 2) rc = -1; }
+        else if (mtype == 0x0008) {
+            if (msize < 18 || d[0] != 3 || d[1] != 1) rc = -1;                      /* version 3, contiguous */
+            else { n->addr = le(d + 2, 8); n->bytes = le(d + 10, 8); have_layout = 1; }
+        } else if (mtype == 0x0011) { if (msize < 16) rc = -1; else { stab_bt = le(d, 8); stab_heap = le(d + 8, 8); n->is_group = 1; } }
+        else if (mtype == 0x000C) {                                                   /* attribute v1: kept so that the model is complete */
+            if (msize < 8 || d[0] != 1) { rc = -1; break; }
+            const size_t nsz = (size_t)le(d + 2, 2), tsz = (size_t)le(d + 4, 2), ssz = (size_t)le(d + 6, 2);
+            size_t q = 8;
+            h5attr a;
+            memset(&a, 0, sizeof a);
+            if (nsz < 1 || nsz > sizeof a.name || q + (nsz + 7) / 8 * 8 + (tsz + 7) / 8 * 8 + (ssz + 7) / 8 * 8 > msize || d[q + nsz - 1] != 0) { rc = -1; break; }
+            memcpy(a.name, d + q, nsz);
+            q += (nsz + 7) / 8 * 8;
+            size_t u;
+            if (rd_datatype(d + q, tsz, &a.type, &u) || u != tsz) { rc = -1; break; }
+            q += (tsz + 7) / 8 * 8;
+            if (rd_dataspace(d + q, ssz, &a.rank, a.dims)) { rc = -1; break; }
+            q += (ssz + 7) / 8 * 8;
+            a.bytes = a.type.size;
+            for (int k = 0; k < a.rank; ++k) a.bytes *= (size_t)a.dims[k];
+            if (q + a.bytes > msize) { rc = -1; break; }
+            a.data = malloc(a.bytes ? a.bytes : 1);
+            memcpy(a.data, d + q, a.bytes);
+            n->attr = (h5attr*)realloc(n->attr, sizeof(h5attr) * (size_t)(n->nattr + 1));
+            n->attr[n->nattr++] = a;
+        } else if (mtype != 0) rc = -1;                                               /* nothing else is written by this library */
+        p += 8 + msize;
+        ++seen;
+    }
+    if (!rc && (p != hsize || seen != nmsg)) rc = -1;
+    free(b);
+    if (rc) return -1;
+    if (n->is_group) {
+        unsigned char hp[32];
+        if (rd_at(r, stab_heap, hp, 32) || memcmp(hp, "HEAP", 4) || hp[4] != 0) return -1;
+        if (rd_btree(r, stab_bt, le(hp + 24, 8), le(hp + 8, 8), n, -1)) return -1;
+    } else {
+        if (!have_space || !have_type || !have_layout) return -1;
+        uint64_t want = n->type.size;
+        for (int d = 0; d < n->rank; ++d) want *= n->dims[d];
+        if (want != n->bytes || n->addr > r->eof || n->bytes > r->eof - n->addr) return -1;
+    }
+    --r->depth;
+    return 0;
+}
+/* parses a file written by this library (or any HDF5 file restricted to the same structures) into the model */
+static h5node* load_tree(FILE* fp) {
+    unsigned char sb[96];
+    static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+    if (fseek(fp, 0, SEEK_SET) || fread(sb, 1, 96, fp) != 96 || memcmp(sb, sig, 8)) return NULL;
+    if (sb[8] != 0 || sb[9] != 0 || sb[10] != 0 || sb[12] != 0 || sb[13] != 8 || sb[14] != 8) return NULL;   /* superblock v0, 8-byte offsets / lengths */
+    h5rd r;
+    memset(&r, 0, sizeof r);
+    r.fp = fp;
+    r.leaf_k = (unsigned)le(sb + 16, 2); r.int_k = (unsigned)le(sb + 18, 2);
+    r.eof = le(sb + 40, 8);
+    if (le(sb + 24, 8) != 0 || r.leaf_k == 0 || r.int_k == 0) return NULL;
+    h5node* root = (h5node*)calloc(1, sizeof(h5node));
+    root->name = strdup("");
+    if (rd_object(&r, le(sb + 64, 8), root) || !root->is_group) { free_node(root); return NULL; }
+    return root;
+}
+
 /* ------------------------------------------------------------------------------------------------ files */
 static h5file* registry_find(const char* path) {
     for (int i = 0; i < 64; ++i) if (g_files[i] && !strcmp(g_files[i]->path, path)) return g_files[i];
@@ -326,18 +504,36 @@ hid_t H5Fcreate(const char* name, unsigned flags, hid_t fcpl, hid_t fapl) {
     return new_id(K_FILE, f, f, f->root);
 }
 hid_t H5Fopen(const char* name, unsigned flags, hid_t fapl) {
-    (void)flags; (void)fapl;
+    (void)fapl;
     h5file* f = registry_find(name);
-    if (!f || f->open) return -1;          /* only files this process created (the reference's save cadence) */
-    f->fp = fopen(name, "rb+");
-    if (!f->fp) return -1;
-    f->open = 1;
+    if (f) {                               /* a file this process created: reopened for the next save (hdf5_funcs.c:538) */
+        if (f->open) return -1;
+        f->fp = fopen(name, "rb+");
+        if (!f->fp) return -1;
+        f->open = 1;
+        return new_id(K_FILE, f, f, f->root);
+    }
+    if (flags != H5F_ACC_RDONLY) return -1;        /* files of other processes are only read */
+    FILE* fp = fopen(name, "rb");
+    if (!fp) return -1;
+    h5node* root = load_tree(fp);
+    if (!root) { fclose(fp); return -1; }
+    f = (h5file*)calloc(1, sizeof *f);
+    snprintf(f->path, sizeof f->path, "%s", name);
+    f->fp = fp; f->root = root; f->open = 1; f->readonly = 1;
     return new_id(K_FILE, f, f, f->root);
 }
 herr_t H5Fclose(hid_t file) {
     h5obj* o = get(file, K_FILE);
     if (!o) return -1;
     h5file* f = (h5file*)o->ptr;
+    if (f->readonly) {                     /* not in the registry: the model goes with the handle */
+        fclose(f->fp);
+        free_node(f->root);
+        free(f);
+        drop(file);
+        return 0;
+    }
     int rc = flush_metadata(f);
     fclose(f->fp);
     f->fp = NULL;
@@ -353,7 +549,7 @@ hid_t H5Gcreate(hid_t loc, const char* name, hid_t lcpl, hid_t gcpl, hid_t gapl)
     h5node* from = loc_node(loc, &f);
     if (!from) return -1;
     h5node* parent = walk(f, from, name, &last, &len);
-    if (!parent || !len || find_child(parent, last, len)) return -1;
+    if (f->readonly || !parent || !len || find_child(parent, last, len)) return -1;
     return new_id(K_GROUP, add_child(parent, last, len, 1), f, NULL);
 }
 hid_t H5Gopen(hid_t loc, const char* name, hid_t gapl) {
@@ -425,7 +621,7 @@ hid_t H5Dcreate(hid_t loc, const char* name, hid_t type, hid_t space, hid_t lcpl
     h5node* from = loc_node(loc, &f);
     h5obj* so = get(space, K_SPACE);
     h5t t;
-    if (!from || !so || resolve_type(type, &t)) return -1;
+    if (!from || f->readonly || !so || resolve_type(type, &t)) return -1;
     h5node* parent = walk(f, from, name, &last, &len);
     if (!parent || !len || find_child(parent, last, len)) return -1;
     h5space* s = (h5space*)so->ptr;
@@ -459,13 +655,14 @@ static uint64_t sel_offset(const h5space* s, uint64_t e) {
     }
     return off;
 }
-herr_t H5Dwrite(hid_t dset, hid_t mem_type, hid_t mem_space, hid_t file_space, hid_t dxpl, const void* buf) {
-    (void)dxpl;
+/* moves the selected elements between the dataset's contiguous storage and a buffer (no type conversion) */
+static herr_t transfer(hid_t dset, hid_t mem_type, hid_t mem_space, hid_t file_space, void* rbuf, const void* wbuf) {
     h5obj* o = get(dset, K_DSET);
     h5t mt;
-    if (!o || !buf || resolve_type(mem_type, &mt)) return -1;
+    if (!o || (!rbuf && !wbuf) || resolve_type(mem_type, &mt)) return -1;
     h5node* n = (h5node*)o->ptr;
     h5file* f = o->file;
+    if (wbuf && f->readonly) return -1;
     if (mt.size != n->type.size || mt.kind != n->type.kind) return -1;          /* no conversions */
     h5space whole;
     memset(&whole, 0, sizeof whole);
@@ -490,9 +687,46 @@ herr_t H5Dwrite(hid_t dset, hid_t mem_type, hid_t mem_space, hid_t file_space, h
     for (uint64_t e = 0; e < nsel; e += run) {
         const uint64_t fo = sel_offset(fs, e), mo = sel_offset(ms, e);
         if (fseek(f->fp, (long)(n->addr + fo * es), SEEK_SET) != 0) return -1;
-        if (fwrite((const char*)buf + mo * es, es, (size_t)run, f->fp) != (size_t)run) return -1;
+        if (wbuf) { if (fwrite((const char*)wbuf + mo * es, es, (size_t)run, f->fp) != (size_t)run) return -1; }
+        else {
+            /* storage that was allocated but never written lies beyond the data written so far: it reads back as zeros */
+            const size_t got = fread((char*)rbuf + mo * es, es, (size_t)run, f->fp);
+            if (got != (size_t)run) memset((char*)rbuf + (mo + got) * es, 0, ((size_t)run - got) * es);
+        }
     }
     return 0;
+}
+herr_t H5Dwrite(hid_t dset, hid_t mem_type, hid_t mem_space, hid_t file_space, hid_t dxpl, const void* buf) {
+    (void)dxpl;
+    return buf ? transfer(dset, mem_type, mem_space, file_space, NULL, buf) : -1;
+}
+herr_t H5Dread(hid_t dset, hid_t mem_type, hid_t mem_space, hid_t file_space, hid_t dxpl, void* buf) {
+    (void)dxpl;
+    return buf ? transfer(dset, mem_type, mem_space, file_space, buf, NULL) : -1;
+}
+hid_t H5Dopen(hid_t loc, const char* name, hid_t dapl) {
+    (void)dapl;
+    h5file* f; const char* last; size_t len;
+    h5node* from = loc_node(loc, &f);
+    if (!from) return -1;
+    h5node* parent = walk(f, from, name, &last, &len);
+    h5node* n = (parent && len) ? find_child(parent, last, len) : NULL;
+    if (!n || n->is_group) return -1;
+    return new_id(K_DSET, n, f, NULL);
+}
+hid_t H5Dget_space(hid_t dset) {
+    h5obj* o = get(dset, K_DSET);
+    if (!o) return -1;
+    const h5node* n = (const h5node*)o->ptr;
+    return H5Screate_simple(n->rank, n->dims, NULL);
+}
+int H5Sget_simple_extent_ndims(hid_t space) { h5obj* o = get(space, K_SPACE); return o ? ((h5space*)o->ptr)->rank : -1; }
+int H5Sget_simple_extent_dims(hid_t space, hsize_t* dims, hsize_t* maxdims) {
+    h5obj* o = get(space, K_SPACE);
+    if (!o) return -1;
+    const h5space* s = (const h5space*)o->ptr;
+    for (int d = 0; d < s->rank; ++d) { if (dims) dims[d] = s->dims[d]; if (maxdims) maxdims[d] = s->dims[d]; }
+    return s->rank;
 }
 herr_t H5Dclose(hid_t dset) { if (!get(dset, K_DSET)) return -1; drop(dset); return 0; }
 
@@ -514,7 +748,7 @@ hid_t H5Acreate(hid_t loc, const char* name, hid_t type, hid_t space, hid_t acpl
     if (!n) { h5obj* o = get(loc, K_DSET); if (o) { n = (h5node*)o->ptr; f = o->file; } }
     h5obj* so = get(space, K_SPACE);
     h5t t;
-    if (!n || !so || resolve_type(type, &t) || strlen(name) > 63) return -1;
+    if (!n || (f && f->readonly) || !so || resolve_type(type, &t) || strlen(name) > 63) return -1;
     for (int i = 0; i < n->nattr; ++i) if (!strcmp(n->attr[i].name, name)) return -1;
     n->attr = (h5attr*)realloc(n->attr, sizeof(h5attr) * (size_t)(n->nattr + 1));
     h5attr* a = &n->attr[n->nattr];

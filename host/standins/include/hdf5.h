@@ -4,7 +4,8 @@
  * from this image; with this header the reference's OWN hdf5_funcs.c compiles unmodified and produces its own file
  * layout (hdf5_funcs.c:172-206 datasets, :1254-1279 attributes, :1058-1165 end-of-run series).  A deployment that has
  * libhdf5 simply puts the real <hdf5.h> first on the include path.  Single process: the MPI-IO property calls are
- * accepted and ignored. */
+ * accepted and ignored.  Plus the five read-side calls the restart hook uses (H5Dopen, H5Dread, H5Dget_space,
+ * H5Sget_simple_extent_ndims / _dims) on files opened with H5F_ACC_RDONLY. */
 #ifndef NSB200_H5LITE_HDF5_H
 #define NSB200_H5LITE_HDF5_H
 #include <stddef.h>
@@ -21,6 +22,7 @@ typedef long long hssize_t;
 
 #define H5P_DEFAULT ((hid_t)0)
 #define H5S_ALL ((hid_t)0)
+#define H5F_ACC_RDONLY 0x0000u
 #define H5F_ACC_RDWR 0x0001u
 #define H5F_ACC_TRUNC 0x0002u
 typedef enum { H5S_SELECT_SET = 0 } H5S_seloper_t;
@@ -53,6 +55,12 @@ herr_t H5Tclose(hid_t type);
 
 hid_t H5Dcreate(hid_t loc, const char* name, hid_t type, hid_t space, hid_t lcpl, hid_t dcpl, hid_t dapl);
 herr_t H5Dwrite(hid_t dset, hid_t mem_type, hid_t mem_space, hid_t file_space, hid_t dxpl, const void* buf);
+/* read side (restart from a saved state, host/nsb200_hooks.c; not called by the reference's hdf5_funcs.c) */
+hid_t H5Dopen(hid_t loc, const char* name, hid_t dapl);
+herr_t H5Dread(hid_t dset, hid_t mem_type, hid_t mem_space, hid_t file_space, hid_t dxpl, void* buf);
+hid_t H5Dget_space(hid_t dset);
+int H5Sget_simple_extent_ndims(hid_t space);
+int H5Sget_simple_extent_dims(hid_t space, hsize_t* dims, hsize_t* maxdims);
 herr_t H5Dclose(hid_t dset);
 
 hid_t H5Acreate(hid_t loc, const char* name, hid_t type, hid_t space, hid_t acpl, hid_t aapl);

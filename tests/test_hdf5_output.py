@@ -42,6 +42,29 @@ def test_h5lite_writer_round_trip(ngroups):
         assert np.array_equal(f.read("/Time"), [0.0, 0.5, 1.0])
 
 
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="gcc not available")
+@pytest.mark.parametrize("ngroups", [1, 3, 700])
+def test_h5lite_reads_files_of_another_process(ngroups):
+    """Read side (restart from a saved state): tests/h5lite_reader.c opens, in its own process, the file the writer driver
+    produced - read-only open of a foreign file, the walk to the last /Iter_%05d group (through a multi-level B-tree at 700
+    groups), whole-dataset and x-slab H5Dread of the compound u_hat, f64 and i32 datasets; every check has its own exit code.
+    A file truncated inside its metadata block, and one that is not HDF5, must be refused."""
+    with tempfile.TemporaryDirectory() as d:
+        inc, src = "-I" + os.path.join(ROOT, "host", "standins", "include"), os.path.join(ROOT, "host", "standins", "h5lite.c")
+        wr, rd, path = os.path.join(d, "wr"), os.path.join(d, "rd"), os.path.join(d, "t.h5")
+        subprocess.run(["gcc", "-O2", inc, os.path.join(ROOT, "tests", "h5lite_driver.c"), src, "-o", wr], check=True)
+        subprocess.run(["gcc", "-O2", inc, os.path.join(ROOT, "tests", "h5lite_reader.c"), src, "-lm", "-o", rd], check=True)
+        subprocess.run([wr, path, str(ngroups)], check=True)
+        assert subprocess.run([rd, path, str(ngroups)]).returncode == 0
+        blob = open(path, "rb").read()
+        cut = os.path.join(d, "cut.h5")
+        open(cut, "wb").write(blob[:len(blob) - 64])
+        assert subprocess.run([rd, cut, str(ngroups)]).returncode == 3        # H5Fopen refuses it
+        junk = os.path.join(d, "junk.h5")
+        open(junk, "wb").write(b"not an hdf5 file" * 64)
+        assert subprocess.run([rd, junk, str(ngroups)]).returncode == 3
+
+
 def solver_files(exe, d, extra_env=None):
     g = np.load(os.path.join(G, "ref_main_tg32.npz"))
     n = int(g["n"])

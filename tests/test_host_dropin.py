@@ -39,6 +39,47 @@ def test_cpu_control_binary_matches_golden():
     assert np.abs(u - g["u_final"]).max() <= 1e-13 * np.abs(g["u_final"]).max()
 
 
+REF_HDRS = "/tmp/nsb200_ref_build"          # patched copy of the reference sources made by `make -C host` (build())
+
+
+@pytest.mark.skipif(not (os.path.exists(CPU) and os.path.exists(os.path.join(REF_HDRS, "data_types.h"))),
+                    reason="needs host/_build/solver_cpu and the reference headers (this container only)")
+def test_restart_hook_reads_the_references_own_hdf5_file():
+    """`-i TESTING -z Main_HDF_Data.h5`: the restart branch of host/nsb200_hooks.c, driven on the CPU through
+    tests/hooks_restart_harness.c, must hand every rank its x-slab of the LAST saved u_hat of a file that the reference's
+    own writer (hdf5_funcs.c in the all-CPU control binary) produced in another process; raw dumps keep working."""
+    with tempfile.TemporaryDirectory() as d:
+        g, main, _ = solver_files(CPU, d)
+        n = int(g["n"])
+        import glob
+        path = glob.glob(os.path.join(d, "SIM_DATA_*", "Main_HDF_Data.h5"))[0]
+        last = sorted(k for k in main.root.children if k.startswith("Iter_"))[-1]
+        u = main.read("/" + last + "/u_hat")
+        u = np.ascontiguousarray(u["r"] + 1j * u["i"])
+        assert np.abs(u).max() > 0
+        exe = os.path.join(d, "harness")
+        st = os.path.join(ROOT, "host", "standins")
+        subprocess.run(["gcc", "-O1", "-w", "-D__NAVIER", "-D__SYS_MEASURES", "-D__MODES", "-D__VORT_FOUR", "-D__ENRG_SPECT", "-D__ENST_SPECT",
+                        "-I" + os.path.join(st, "include"), "-I" + REF_HDRS, "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "hooks_restart_harness.c"), os.path.join(st, "h5lite.c"), os.path.join(st, "mpi_shim.c"),
+                        "-L" + os.path.join(ROOT, "3d_navier_stokes_b200"), "-lnsb200", "-lm",
+                        "-Wl,-rpath," + os.path.join(ROOT, "3d_navier_stokes_b200"), "-o", exe], check=True)
+        raw = os.path.join(d, "state.bin")
+        u.tofile(raw)
+        for src in (path, raw):
+            for nranks in (1, 2):
+                for rank in range(nranks):
+                    out = os.path.join(d, "slab.bin")
+                    p = subprocess.run([exe, src, str(n), str(nranks), str(rank), out], capture_output=True, text=True, timeout=120)
+                    assert p.returncode == 0, p.stdout[-1000:] + p.stderr[-1000:]
+                    got = np.fromfile(out, dtype=np.complex128).reshape(n // nranks, n, n // 2 + 1, 3)
+                    x0 = rank * (n // nranks)
+                    assert np.array_equal(got, u[x0:x0 + n // nranks])
+        # wrong grid size: the reference-style error, exit(1)
+        p = subprocess.run([exe, path, str(2 * n), "1", "0", os.path.join(d, "x.bin")], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 1 and "does not have the shape" in p.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(B200), reason="host/_build/solver_b200 not built (make -C host)")
 def test_reference_program_on_gpu_matches_golden():
