@@ -771,6 +771,26 @@ herr_t H5Awrite(hid_t attr, hid_t mem_type, const void* buf) {
     memcpy(a->data, buf, a->bytes);
     return 0;
 }
+/* read side: attributes of a group, file root or dataset by name */
+hid_t H5Aopen(hid_t loc, const char* name, hid_t aapl) {
+    (void)aapl;
+    h5file* f = NULL;
+    h5node* n = loc_node(loc, &f);
+    if (!n) { h5obj* o = get(loc, K_DSET); if (o) { n = (h5node*)o->ptr; f = o->file; } }
+    if (!n) return -1;
+    for (int i = 0; i < n->nattr; ++i)
+        if (!strcmp(n->attr[i].name, name)) return new_id(K_ATTR, n, f, (h5node*)(intptr_t)i);
+    return -1;
+}
+herr_t H5Aread(hid_t attr, hid_t mem_type, void* buf) {
+    h5obj* o = get(attr, K_ATTR);
+    h5t mt;
+    if (!o || !buf || resolve_type(mem_type, &mt)) return -1;
+    const h5attr* a = &((h5node*)o->ptr)->attr[(int)(intptr_t)o->owner];
+    if (mt.size != a->type.size || mt.kind != a->type.kind) return -1;
+    memcpy(buf, a->data, a->bytes);
+    return 0;
+}
 herr_t H5Aclose(hid_t attr) { if (!get(attr, K_ATTR)) return -1; drop(attr); return 0; }
 
 /* ------------------------------------------------------------------------------------------------ property lists */

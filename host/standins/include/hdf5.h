@@ -4,8 +4,8 @@
  * from this image; with this header the reference's OWN hdf5_funcs.c compiles unmodified and produces its own file
  * layout (hdf5_funcs.c:172-206 datasets, :1254-1279 attributes, :1058-1165 end-of-run series).  A deployment that has
  * libhdf5 simply puts the real <hdf5.h> first on the include path.  Single process: the MPI-IO property calls are
- * accepted and ignored.  Plus the five read-side calls the restart hook uses (H5Dopen, H5Dread, H5Dget_space,
- * H5Sget_simple_extent_ndims / _dims) on files opened with H5F_ACC_RDONLY. */
+ * accepted and ignored.  Plus the read-side calls the restart hook uses (H5Dopen, H5Dread, H5Dget_space,
+ * H5Sget_simple_extent_ndims / _dims, H5Aopen, H5Aread) on files opened with H5F_ACC_RDONLY. */
 #ifndef NSB200_H5LITE_HDF5_H
 #define NSB200_H5LITE_HDF5_H
 #include <stddef.h>
@@ -65,6 +65,8 @@ herr_t H5Dclose(hid_t dset);
 
 hid_t H5Acreate(hid_t loc, const char* name, hid_t type, hid_t space, hid_t acpl, hid_t aapl);
 herr_t H5Awrite(hid_t attr, hid_t mem_type, const void* buf);
+hid_t H5Aopen(hid_t loc, const char* name, hid_t aapl);      /* read side */
+herr_t H5Aread(hid_t attr, hid_t mem_type, void* buf);
 herr_t H5Aclose(hid_t attr);
 
 hid_t H5Pcreate(hid_t cls);

@@ -60,6 +60,17 @@ int main(int argc, char** argv) {
     if (k[0] != 0 || k[3] != 3 || k[4] != -3 || k[6] != -1) return 18;
     H5Dclose(d);
     if (H5Dopen(f, "/Iter_00000", H5P_DEFAULT) >= 0) return 19;                            /* a group is not a dataset */
+    snprintf(name, sizeof name, "/Iter_%05d", last);
+    hid_t g = H5Gopen(f, name, H5P_DEFAULT);
+    hid_t a = H5Aopen(g, "TimeValue", H5P_DEFAULT);
+    double tv = -1.0, ts = -1.0;
+    if (g < 0 || a < 0 || H5Aread(a, H5T_NATIVE_DOUBLE, &tv) < 0 || tv != 0.5 * last) return 21;
+    H5Aclose(a);
+    a = H5Aopen(g, "TimeStep", H5P_DEFAULT);
+    if (a < 0 || H5Aread(a, H5T_NATIVE_DOUBLE, &ts) < 0 || ts != 1e-3) return 22;
+    H5Aclose(a);
+    if (H5Aopen(g, "NoSuchAttribute", H5P_DEFAULT) >= 0) return 23;
+    H5Gclose(g);
     H5Tclose(ct);
     if (H5Fclose(f) < 0) return 20;
     return 0;
